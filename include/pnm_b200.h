@@ -1,0 +1,187 @@
+/*
+ * pnm_b200.h -- C ABI of libpnm_b200.so: pynmap's particle-projection hot path on B200 (sm_100a).
+ *
+ * The reference (emsellem/pynmap) has no FFI layer: the path is four Python functions whose
+ * arithmetic lives in numpy / astropy library calls.  Each entry point below replaces the BODY
+ * of one of those calls; the Python host layer (pynmap_b200/*.py) keeps the reference's
+ * signatures and binds these symbols with ctypes.  Citations are file:line in emsellem/pynmap.
+ *
+ *   pnm_rotate            np.dot(mat, pos.T).T                 pynmap/rotation.py:115-117, :67-69
+ *   pnm_grid_create       np.linspace bin edges                pynmap/grid.py:121-124, :196-199, :243-245
+ *   pnm_project_bin       rotate_mat + 3x np.histogram2d       pynmap/rotation.py:73-119 + grid.py:126-131
+ *                         + np.histogramdd                     + grid.py:252-259 (one read of the particles)
+ *   pnm_bin_points        np.histogram2d x3 / x2, histogramdd  pynmap/grid.py:126-131, :200-201, :259
+ *   pnm_finalize_vmaps    V = S1/S0, S = sqrt(S2/S0 - V*V)     pynmap/grid.py:133-138
+ *   pnm_finalize_map      D = DW/W                             pynmap/grid.py:203-205
+ *   pnm_finalize_cube     weights-histogram -> float64 cube    pynmap/grid.py:259
+ *   pnm_smooth_cube       astropy convolve per velocity slice  pynmap/losvd.py:127-135
+ *   pnm_cube_moments      moment012 per spaxel                 pynmap/losvd.py:41-51, misc_functions.py:70-90
+ *   pnm_absmax            (new) bound for the fixed-point scale
+ *   pnm_project_host      snapshot.rotate + velocity_moments + create_losvds from HOST arrays
+ *                                                              pynmap/pynmap.py:246-285, :319-340, :439-455
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PNM_E* code otherwise; the message is
+ *     available from pnm_last_error() (thread local);
+ *   - all particle / accumulator / output pointers are DEVICE pointers unless the name ends in
+ *     _host; the library never allocates or frees caller-visible memory.  The only internal
+ *     allocations are the small edge tables owned by a pnm_grid (and the staging ring of
+ *     pnm_project_host);
+ *   - all work is enqueued on the cudaStream_t passed as `stream` (a void* here so that the
+ *     header needs no CUDA include); nothing synchronises except pnm_project_host;
+ *   - there is no CPU fallback: every entry point fails with PNM_ECUDA when no sm_100 device
+ *     is usable.
+ */
+#ifndef PNM_B200_H
+#define PNM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNM_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define PNM_OK 0
+#define PNM_EINVAL (-1)   /* bad argument (null pointer, size, flag combination) */
+#define PNM_EDTYPE (-2)   /* unsupported dtype */
+#define PNM_ECUDA (-3)    /* CUDA runtime error (message has the cudaError string) */
+#define PNM_ELIMIT (-4)   /* size above a compiled-in limit (edges, taps, chain length) */
+
+/* particle array dtypes (np.result_type(float32, input) of the reference, rotation.py:115) */
+#define PNM_F32 0
+#define PNM_F64 1
+
+/* accumulator arithmetic */
+#define PNM_ACC_F64 0   /* float64 atomics: <=1e-12 relative vs the sequential float64 sums    */
+#define PNM_ACC_FIXED 1 /* int64 fixed point: order independent, bit-identical on any #GPUs   */
+
+/* which sums one call accumulates */
+#define PNM_SUM_W 1     /* sum w           -> maps slot 0                                     */
+#define PNM_SUM_WD 2    /* sum w*d         -> maps slot 1   (d = v_los or user data)          */
+#define PNM_SUM_WD2 4   /* sum w*(d*d)     -> maps slot 2                                     */
+#define PNM_SUM_CUBE 8  /* (x, y, d) weighted histogram -> cube                               */
+/* With PNM_SUM_W|PNM_SUM_CUBE and PNM_W_FROM_CUBE the map's sum w is not accumulated
+ * directly: particles inside the V range go to the cube only, the others to maps slot 0,
+ * and pnm_finalize_vmaps adds the cube's V-sum back.  One atomic fewer per particle.       */
+#define PNM_W_FROM_CUBE 16
+
+/* mask semantics of the reference */
+#define PNM_MASK_NONE 0
+#define PNM_MASK_AND_NONFINITE 1 /* drop iff mask && !isfinite(d)   grid.py:113-119, :188-194 */
+#define PNM_MASK_PLAIN 2         /* drop iff mask                   grid.py:251-254           */
+
+#define PNM_MAX_EDGES 4097 /* bins + 1 per axis                                              */
+#define PNM_MAX_CHAIN 8    /* compounded rotations applied in registers (rotate(reset=False)) */
+#define PNM_MAX_VIEWS 64   /* viewing angles per particle read                               */
+#define PNM_MAX_TAPS 255   /* Gaussian taps per axis                                         */
+#define PNM_MAP_SLOTS 4    /* interleaved accumulator slots per pixel: S0, S1, S2, reserved  */
+
+typedef struct pnm_grid pnm_grid; /* opaque: edge tables on one device */
+
+int pnm_version(void);
+const char* pnm_last_error(void);
+/* number of usable sm_100 devices (0 if none / no driver) */
+int pnm_device_count(void);
+
+/* ---- a1: materialising rotation (rotation.py:115-117) -------------------------------------
+ * out = fl(fma(m[3r+2], z, fma(m[3r+1], y, fl(m[3r]*x)))) per row r, in `dtype` arithmetic,
+ * mat9_host = row-major float32 3x3 on the HOST.  In-place (ox==x ...) is allowed.          */
+int pnm_rotate(const void* x, const void* y, const void* z, void* ox, void* oy, void* oz,
+               int64_t n, int dtype, const float* mat9_host, void* stream);
+
+/* ---- grid (edge tables) -------------------------------------------------------------------
+ * edges_*_host: float64 arrays of n*+1 monotonically increasing edges built by the host with
+ * the reference's own numpy expression (grid.py:121-124).  nv == 0 / edges_v_host == NULL: no
+ * velocity axis.  Bin rule = numpy histogramdd: edges[i] <= x < edges[i+1], last edge
+ * inclusive, NaN / out-of-range dropped; comparisons exact in float64.                       */
+int pnm_grid_create(int32_t nx, const double* edges_x_host, int32_t ny, const double* edges_y_host,
+                    int32_t nv, const double* edges_v_host, pnm_grid** out);
+int pnm_grid_destroy(pnm_grid* g);
+
+/* accumulator geometry for a grid: number of 8-byte elements in the maps and cube accumulators */
+int64_t pnm_maps_acc_elems(const pnm_grid* g); /* ny*nx*PNM_MAP_SLOTS */
+int64_t pnm_cube_acc_elems(const pnm_grid* g); /* nx*ny*nv            */
+
+/* ---- fused rotate + project + bin (a1+a2+a3+a4) ---------------------------------------------
+ * For each of `nviews` views: apply `nchain` float32 matrices in sequence to (x,y,z) and
+ * (vx,vy,vz) (each step rounded like pnm_rotate), take x' = pos'[0], y' = pos'[1],
+ * d = vel'[2], then accumulate the sums selected by `sums` with weights w (NULL = 1):
+ *   acc_maps [view][iy][ix][4]   8-byte elements (double or int64 by acc_mode)
+ *   acc_cube [view][ix][iy][iv]  8-byte elements
+ * mats_host: float32 [nviews][nchain][9] on the HOST.  scales3_host (FIXED only): the three
+ * power-of-two scales for w, w*d, w*d*d.  Accumulators must be zeroed by the caller (or hold
+ * earlier partial sums: calls add).  mask: optional uint8 per particle.                       */
+int pnm_project_bin(const pnm_grid* g, int64_t n, int dtype,
+                    const void* x, const void* y, const void* z,
+                    const void* vx, const void* vy, const void* vz,
+                    const void* w, const uint8_t* mask, int mask_mode,
+                    const float* mats_host, int nchain, int nviews,
+                    int sums, int acc_mode, const double* scales3_host,
+                    void* acc_maps, void* acc_cube, void* stream);
+
+/* ---- un-fused binning of already projected points (grid.py:70-262) ------------------------- */
+int pnm_bin_points(const pnm_grid* g, int64_t n, int dtype,
+                   const void* x, const void* y, const void* d, const void* w,
+                   const uint8_t* mask, int mask_mode,
+                   int sums, int acc_mode, const double* scales3_host,
+                   void* acc_maps, void* acc_cube, void* stream);
+
+/* ---- finalisation (grid.py:133-138, :203-205) -----------------------------------------------
+ * Reads acc_maps (and acc_cube when `sums` has PNM_W_FROM_CUBE), writes planar float64
+ * (ny, nx) maps.  Any output pointer may be NULL.
+ *   vmaps: M = S0, V = S1/S0, S = sqrt(S2/S0 - V*V) where S0 != 0, else 0
+ *   map  : W = S0, D = S1/S0 where S0 != 0, DW = S1                                            */
+int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_cube,
+                       int sums, int acc_mode, const double* scales3_host,
+                       double* M, double* V, double* S, double* S1, double* S2, void* stream);
+int pnm_finalize_map(const pnm_grid* g, const void* acc_maps, int acc_mode,
+                     const double* scales3_host, double* W, double* D, double* DW, void* stream);
+/* FIXED accumulators -> float64 cube, in place allowed (cube_out == acc_cube) */
+int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int acc_mode, double scale_w,
+                      double* cube_out, void* stream);
+
+/* ---- a5: separable Gaussian smoothing of every velocity slice (losvd.py:127-135) ------------
+ * cube_in/out/work: float64 [nx][ny][nv], three distinct buffers (work = scratch of the same
+ * size, owned by the caller).  taps0_host act along array axis 0, taps1_host along axis 1 (odd
+ * counts, already normalised, built on the host in float64).  Zero fill outside the array
+ * (astropy convolve boundary='fill', fill_value=0).                                           */
+int pnm_smooth_cube(const double* cube_in, double* cube_out, double* work,
+                    int32_t nx, int32_t ny, int32_t nv,
+                    const double* taps0_host, int32_t ntaps0,
+                    const double* taps1_host, int32_t ntaps1, void* stream);
+
+/* ---- f1: per-spaxel moments of the cube (losvd.py:41-51, misc_functions.py:70-90) ----------
+ * mom0 = sum_k c, mom1 = sum_k v c / mom0, mom2 = sqrt(sum_k v^2 c / mom0 - mom1^2); (nx, ny).
+ * An all-zero spaxel gives (0, 0, empty_m2), empty_m2 = min(diff(binv)) / 3 from the host.     */
+int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv,
+                     const double* binv_dev, double empty_m2,
+                     double* mom0, double* mom1, double* mom2, void* stream);
+
+/* ---- max |a[i]| over n elements -> out_dev[0] (float64, device); used to pick FIXED scales -- */
+int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream);
+
+/* ---- host-buffer path: what a reference user calls, end to end -------------------------------
+ * Particle arrays live in HOST memory (pinned or pageable).  The call streams them through an
+ * internal device staging ring in chunks, overlapping the copies with pnm_project_bin, then
+ * finalises and copies the results back to HOST buffers (any may be NULL):
+ *   M, V, S : float64 (ny, nx);   cube : float64 (nx, ny, nv).
+ * Synchronous: returns when the outputs are in host memory.  device = CUDA ordinal.          */
+int pnm_project_host(int device, int64_t n, int dtype,
+                     const void* x_host, const void* y_host, const void* z_host,
+                     const void* vx_host, const void* vy_host, const void* vz_host,
+                     const void* w_host,
+                     const float* mats_host, int nchain,
+                     int32_t nx, const double* edges_x_host, int32_t ny, const double* edges_y_host,
+                     int32_t nv, const double* edges_v_host,
+                     int acc_mode, const double* scales3_host,
+                     double* M_host, double* V_host, double* S_host, double* cube_host);
+/* frees the staging ring pnm_project_host keeps between calls */
+int pnm_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNM_B200_H */

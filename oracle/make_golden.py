@@ -1,0 +1,171 @@
+"""TEST INFRASTRUCTURE ONLY -- regenerates tests/golden/*.npz by executing the UNMODIFIED
+reference (``/root/reference/pynmap``) under ``oracle/refshim.py``.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python oracle/make_golden.py
+
+The reference has no tests, fixtures or golden vectors of its own, so
+these files ARE the pin: inputs and the reference's outputs for every function on the hot
+path (rotation.py:73-119, :14-71; grid.py:70-262; losvd.py:94-141; pynmap.py:246-455),
+including the quirks listed in SURVEY.md 8(c).  Everything is stored bit-exactly (npz).
+numpy 2.3.5 / scipy 1.18.1 produced the committed vectors.  The smoothing vectors go through
+the shim's restatement of astropy (astropy is absent) and are therefore NOT a pin of astropy.
+"""
+import contextlib
+import io
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from oracle.refshim import load_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def toy_snapshot(n, seed, dtype):
+    """Small exponential disk + bulge in numpy (kpc, km/s); only used to make fixtures."""
+    rng = np.random.default_rng(seed)
+    nb = n // 5
+    nd = n - nb
+    R = rng.gamma(2.0, 3.0, nd)
+    phi = rng.uniform(0, 2 * np.pi, nd)
+    z = 0.3 * np.arctanh(rng.uniform(-0.999, 0.999, nd))
+    vc = 220.0 * R / np.sqrt(R * R + 1.0)
+    sr = 55.0 * np.exp(-R / 6.0) + 5.0
+    vr, vp, vz = sr * rng.standard_normal(nd), vc + sr / np.sqrt(2) * rng.standard_normal(nd), 0.6 * sr * rng.standard_normal(nd)
+    disk_pos = np.stack([R * np.cos(phi), R * np.sin(phi), z], 1)
+    disk_vel = np.stack([vr * np.cos(phi) - vp * np.sin(phi), vr * np.sin(phi) + vp * np.cos(phi), vz], 1)
+    r = 0.5 / np.sqrt(rng.uniform(1e-6, 1, nb) ** (-2.0 / 3.0) - 1.0 + 1e-12)
+    u = rng.standard_normal((nb, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    sig = 120.0 / (1.0 + (r / 0.5) ** 2) ** 0.25
+    pos = np.concatenate([disk_pos, r[:, None] * u])
+    vel = np.concatenate([disk_vel, sig[:, None] * rng.standard_normal((nb, 3))])
+    perm = rng.permutation(n)
+    mass = rng.uniform(0.5, 2.0, n)
+    return pos[perm].astype(dtype), vel[perm].astype(dtype), mass.astype(dtype)
+
+
+def main():
+    ref = load_reference()
+    rot, grid, losvd_mod = ref.rotation, ref.grid, ref.losvd
+    os.makedirs(OUT, exist_ok=True)
+    saved = {}
+
+    def save(name, **arrays):
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+        saved[name] = sum(np.asarray(a).nbytes for a in arrays.values())
+
+    # ---- rotation: float32 / float64 data x python-float / float32 angles x direct / inverse
+    for dt in (np.float32, np.float64):
+        pos, vel, _ = toy_snapshot(1024, 11, dt)
+        pos[7] = [np.inf, 1.0, -2.0]      # non-finite coordinates travel through np.dot
+        pos[9] = [np.nan, 0.0, 0.0]
+        out = {"pos": pos, "vel": vel}
+        for tag, (pa, inc) in {"f64ang": (30.0, 60.0), "f32ang": (np.float32(30.0), np.float32(60.0)),
+                               "odd": (12.3, 77.7)}.items():
+            for direct in (True, False):
+                p, v = rot.rotate_mat(pos, vel, pa, inc, direct)
+                k = "%s_%s" % (tag, "dir" if direct else "inv")
+                out["pos_" + k], out["vel_" + k] = np.ascontiguousarray(p), np.ascontiguousarray(v)
+        p, v = rot.rotateXYZ_mat(pos, vel, 10.0, 20.0, 30.0, rotorder=[2, 0, 1])
+        out["pos_xyz"], out["vel_xyz"] = np.ascontiguousarray(p), np.ascontiguousarray(v)
+        p, _ = rot.rotate_mat(pos, None, 45.0, 45.0)
+        out["pos_novel"] = np.ascontiguousarray(p)
+        save("rotate_%s" % np.dtype(dt).name, **out)
+
+    # ---- KAT: edge inclusivity, NaN / inf dropping, matrices, orientation
+    xk = np.array([-1.5, -0.5, 0.5, 1.5, 1.5000001, -1.5000001, np.nan, np.inf, -np.inf, 0.0])
+    gx, gy, M, V, S = quiet(grid.points_2vmaps, xk, np.zeros_like(xk), np.ones_like(xk), limXY=[-1, 1, -1, 1], nXY=3)
+    vq = np.array([1.0, np.nan, 3.0])
+    _, _, M_nomask, V_nomask, _ = quiet(grid.points_2vmaps, np.zeros(3), np.zeros(3), vq, limXY=[-1, 1, -1, 1], nXY=3)
+    _, _, M_mask, V_mask, _ = quiet(grid.points_2vmaps, np.zeros(3), np.zeros(3), vq, limXY=[-1, 1, -1, 1], nXY=3,
+                                    mask=np.array([True, True, False]))
+    save("kat", x_edge=xk, M_edge=M, V_edge=V, S_edge=S, gridX_edge=gx, gridY_edge=gy,
+         v_quirk=vq, M_nomask=M_nomask, V_nomask=V_nomask, M_mask=M_mask, V_mask=V_mask,
+         mat_f64ang=_matrix(rot, 30.0, 60.0), mat_f32ang=_matrix(rot, np.float32(30.0), np.float32(60.0)))
+
+    # ---- maps and cubes on a toy snapshot, float32 and float64, weighted and not
+    for dt in (np.float32, np.float64):
+        pos, vel, mass = toy_snapshot(12000, 5, dt)
+        p, v = rot.rotate_mat(pos, vel, np.float32(30.0), np.float32(60.0))
+        x, y, d = p[:, 0], p[:, 1], v[:, 2]
+        lim, nxy, limv, nv = [-15, 15, -12, 12], (40, 32), [-400, 400], 20
+        out = {"pos": pos, "vel": vel, "mass": mass, "x": np.ascontiguousarray(x), "y": np.ascontiguousarray(y),
+               "d": np.ascontiguousarray(d), "limXY": np.array(lim, float), "nXY": np.array(nxy), "limV": np.array(limv, float),
+               "nV": np.array(nv)}
+        for wtag, w in (("w", mass), ("u", None)):
+            gx, gy, M, V, S = quiet(grid.points_2vmaps, x, y, d, weights=w, limXY=lim, nXY=nxy)
+            out.update({"vm_%s_M" % wtag: M, "vm_%s_V" % wtag: V, "vm_%s_S" % wtag: S})
+            _, _, W, D, DW = quiet(grid.points_2map, x, y, d, weights=w, limXY=lim, nXY=nxy)
+            out.update({"map_%s_W" % wtag: W, "map_%s_D" % wtag: D, "map_%s_DW" % wtag: DW})
+            L = quiet(grid.points_2losvds, x, y, d, weights=w, limXY=lim, nXY=nxy, limV=limv, nV=nv)
+            out["cube_%s" % wtag] = L.losvd
+        out.update({"gridX": gx, "gridY": gy, "binx": L.binx, "biny": L.biny, "binv": L.binv})
+        # raw sums, for tolerance tests that do not go through the ill-conditioned sigma
+        ex = np.linspace(lim[0] - (lim[1] - lim[0]) / (nxy[0] - 1) / 2., lim[1] + (lim[1] - lim[0]) / (nxy[0] - 1) / 2., nxy[0] + 1)
+        ey = np.linspace(lim[2] - (lim[3] - lim[2]) / (nxy[1] - 1) / 2., lim[3] + (lim[3] - lim[2]) / (nxy[1] - 1) / 2., nxy[1] + 1)
+        out["s1_w"] = np.histogram2d(x, y, [ex, ey], weights=mass * d)[0].T
+        out["s2_w"] = np.histogram2d(x, y, [ex, ey], weights=mass * d ** 2)[0].T
+        out["edges_x"], out["edges_y"] = ex, ey
+        # mask with weights=None on the cube path (the legal combination)
+        msk = np.zeros(x.size, bool)
+        msk[::7] = True
+        out["mask"] = msk
+        out["cube_masked_u"] = quiet(grid.points_2losvds, x, y, d, limXY=lim, nXY=nxy, limV=limv, nV=nv, mask=msk).losvd
+        dq = d.copy()
+        dq[::11] = np.nan
+        out["d_nan"] = dq
+        _, _, Mq, Vq, Sq = quiet(grid.points_2vmaps, x, y, dq, weights=mass, limXY=lim, nXY=nxy, mask=msk)
+        out.update({"vm_q_M": Mq, "vm_q_V": Vq, "vm_q_S": Sq})
+        # smoothing (shim restatement of astropy): equal and unequal widths
+        Lw = losvd_mod.LOSVD(L.binx, L.biny, L.binv, out["cube_w"])
+        c1 = quiet(Lw.convolve_spatial, 1.5, 1.5)
+        c2 = quiet(Lw.convolve_spatial, 1.2, 2.4)
+        c3 = quiet(c1.convolve_spatial, 2.5, 2.0)
+        out.update({"smooth_eq": c1.losvd, "smooth_neq": c2.losvd, "smooth_twice": c3.losvd})
+        quiet(Lw.vmoments)
+        out.update({"mom0": Lw.mom0, "mom1": Lw.mom1, "mom2": Lw.mom2})
+        save("grid_%s" % np.dtype(dt).name, **out)
+
+    # ---- snapshot level: ascii file -> rotate -> velocity_moments / create_map / create_losvds
+    pos, vel, mass = toy_snapshot(4000, 21, np.float64)
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savetxt(os.path.join(tmp, "snap.txt"), np.hstack([pos, vel, mass[:, None]]), fmt="%.17g")
+        snap = quiet(ref.pynmap.snapshot, folder=tmp, snap_name="snap.txt", MLrecipe="none", extra_labels=["mass"], verbose=False)
+        quiet(snap.rotate, PA=30., inclination=60.)
+        vm = quiet(snap.velocity_moments, weight_name="mass", limXY=[-12, 12, -12, 12], nXY=32)
+        mp = quiet(snap.create_map, weight_name="mass", limXY=[-12, 12, -12, 12], nXY=32)
+        lv = quiet(snap.create_losvds, weight_name="mass", limXY=[-12, 12, -12, 12], nXY=16, limV=[-350, 350], nV=20)
+        pos1, vel1 = np.ascontiguousarray(snap.pos), np.ascontiguousarray(snap.vel)
+        quiet(snap.rotate, PA=15., inclination=20., reset=False)         # compounded on rounded coordinates
+        vm2 = quiet(snap.velocity_moments, weight_name="mass", limXY=[-12, 12, -12, 12], nXY=32)
+        pos2 = np.ascontiguousarray(snap.pos)
+        PAs2, incs2 = np.array(snap.PAs), np.array(snap.inclinations)
+    save("snapshot", pos=pos, vel=vel, mass=mass, M=vm.M, V=vm.V, S=vm.S, X=vm.X, Y=vm.Y, W=mp.W, D=mp.D, DW=mp.DW,
+         cube=lv.losvd, binv=lv.binv, pos_rot=pos1, vel_rot=vel1, M2=vm2.M, V2=vm2.V, S2=vm2.S, pos_rot2=pos2,
+         PAs2=PAs2, incs2=incs2)
+
+    for k, v in saved.items():
+        print("%-16s %8.1f kB (uncompressed)" % (k, v / 1e3))
+
+
+def _matrix(rot, pa, inc):
+    """The float32 matrix rotate_mat builds, observed through its action on the unit vectors."""
+    eye = np.eye(3, dtype=np.float32)
+    p, _ = rot.rotate_mat(eye, None, pa, inc)
+    return np.ascontiguousarray(p.T)      # p = (mat . I)^T
+
+
+if __name__ == "__main__":
+    main()

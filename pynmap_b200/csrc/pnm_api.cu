@@ -1,0 +1,358 @@
+// pnm_api.cu -- extern "C" surface of libpnm_b200.so (see include/pnm_b200.h for the contract).
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "pnm_bin.cuh"
+#include "pnm_post.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define PNM_CUDA(call)                                                                       \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess)                                                               \
+            return fail(PNM_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                 \
+    } while (0)
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
+    int64_t blocks = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)pnm::kNumSMs * ctas_per_sm;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// smallest T >= e (lower edges) / the exclusive upper bound equivalent to "<= e" (last edge)
+template <typename T> T thr_lower(double e);
+template <> float thr_lower<float>(double e) {
+    float f = (float)e;
+    if ((double)f < e) f = nextafterf(f, INFINITY);
+    return f;
+}
+template <> double thr_lower<double>(double e) { return e; }
+template <typename T> T thr_last(double e);
+template <> float thr_last<float>(double e) {
+    float f = (float)e;
+    if ((double)f > e) f = nextafterf(f, -INFINITY);   // largest float <= e
+    return nextafterf(f, INFINITY);
+}
+template <> double thr_last<double>(double e) { return nextafter(e, INFINITY); }
+
+}  // namespace
+
+struct pnm_grid {
+    int device;
+    int nx, ny, nv;
+    // per axis: thresholds in both particle dtypes, laid out [x | y | v]
+    float* thr32;
+    double* thr64;
+    double x0, inv_dx, y0, inv_dy, v0, inv_dv;
+};
+
+extern "C" {
+
+// internal: lets pnm_host.cu publish its message through pnm_last_error()
+void pnm_set_last_error_(const char* msg) { snprintf(g_err, sizeof(g_err), "%s", msg ? msg : ""); }
+
+int pnm_version(void) { return PNM_VERSION; }
+const char* pnm_last_error(void) { return g_err; }
+
+int pnm_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------ rotate
+int pnm_rotate(const void* x, const void* y, const void* z, void* ox, void* oy, void* oz,
+               int64_t n, int dtype, const float* mat9_host, void* stream) {
+    if (n < 0 || !mat9_host) return fail(PNM_EINVAL, "pnm_rotate: bad n or matrix");
+    if (n == 0) return PNM_OK;
+    if (!x || !y || !z || !ox || !oy || !oz) return fail(PNM_EINVAL, "pnm_rotate: null array");
+    pnm::Mat9 m;
+    memcpy(m.m, mat9_host, sizeof(m.m));
+    const int grid = grid_for(n, 256, 16);
+    if (dtype == PNM_F32)
+        pnm::k_rotate<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, (const float*)y, (const float*)z,
+                                                                  (float*)ox, (float*)oy, (float*)oz, n, m);
+    else if (dtype == PNM_F64)
+        pnm::k_rotate<double><<<grid, 256, 0, as_stream(stream)>>>((const double*)x, (const double*)y, (const double*)z,
+                                                                   (double*)ox, (double*)oy, (double*)oz, n, m);
+    else
+        return fail(PNM_EDTYPE, "pnm_rotate: dtype %d", dtype);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+// ------------------------------------------------------------------------------------ grid
+int pnm_grid_create(int32_t nx, const double* ex, int32_t ny, const double* ey,
+                    int32_t nv, const double* ev, pnm_grid** out) {
+    if (!out) return fail(PNM_EINVAL, "pnm_grid_create: out is null");
+    *out = nullptr;
+    if (nx < 1 || ny < 1 || !ex || !ey || nv < 0 || (nv > 0 && !ev))
+        return fail(PNM_EINVAL, "pnm_grid_create: bad sizes nx=%d ny=%d nv=%d", nx, ny, nv);
+    if (nx + 1 > PNM_MAX_EDGES || ny + 1 > PNM_MAX_EDGES || nv + 1 > PNM_MAX_EDGES)
+        return fail(PNM_ELIMIT, "pnm_grid_create: more than %d edges on an axis", PNM_MAX_EDGES);
+    const int32_t ns[3] = {nx, ny, nv};
+    const double* es[3] = {ex, ey, ev};
+    for (int a = 0; a < 3; ++a)
+        for (int i = 0; i < ns[a]; ++i)
+            if (!(es[a][i] < es[a][i + 1]))   // numpy raises on non-monotonic bins as well
+                return fail(PNM_EINVAL, "pnm_grid_create: axis %d edges must increase strictly", a);
+
+    const int total = (nx + 1) + (ny + 1) + (nv + 1);
+    std::vector<float> t32(total);
+    std::vector<double> t64(total);
+    int o = 0;
+    for (int a = 0; a < 3; ++a) {
+        if (ns[a] == 0) { t32[o] = 0.f; t64[o] = 0.0; o += 1; continue; }
+        for (int i = 0; i < ns[a]; ++i) { t32[o + i] = thr_lower<float>(es[a][i]); t64[o + i] = es[a][i]; }
+        t32[o + ns[a]] = thr_last<float>(es[a][ns[a]]);
+        t64[o + ns[a]] = thr_last<double>(es[a][ns[a]]);
+        o += ns[a] + 1;
+    }
+    pnm_grid* g = new pnm_grid();
+    g->nx = nx; g->ny = ny; g->nv = nv;
+    g->x0 = ex[0]; g->inv_dx = nx / (ex[nx] - ex[0]);
+    g->y0 = ey[0]; g->inv_dy = ny / (ey[ny] - ey[0]);
+    g->v0 = nv ? ev[0] : 0.0; g->inv_dv = nv ? nv / (ev[nv] - ev[0]) : 0.0;
+    g->thr32 = nullptr; g->thr64 = nullptr;
+    cudaError_t e = cudaGetDevice(&g->device);
+    if (e == cudaSuccess) e = cudaMalloc(&g->thr32, total * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&g->thr64, total * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(g->thr32, t32.data(), total * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(g->thr64, t64.data(), total * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(g->thr32); cudaFree(g->thr64); delete g;
+        return fail(PNM_ECUDA, "pnm_grid_create: %s", cudaGetErrorString(e));
+    }
+    *out = g;
+    return PNM_OK;
+}
+
+int pnm_grid_destroy(pnm_grid* g) {
+    if (!g) return PNM_OK;
+    cudaFree(g->thr32);
+    cudaFree(g->thr64);
+    delete g;
+    return PNM_OK;
+}
+
+int64_t pnm_maps_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * PNM_MAP_SLOTS : 0; }
+int64_t pnm_cube_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * g->nv : 0; }
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------ binning
+namespace {
+
+template <typename T, bool FUSED>
+int launch_bin(const pnm::BinParams& p, int acc_mode, cudaStream_t st) {
+    const size_t smem = (size_t)((p.nx + 1) + (p.ny + 1) + (p.nv + 1)) * sizeof(T);
+    bool aligned = true;
+    const void* ptrs[7] = {p.x, p.y, p.z, p.vx, p.vy, p.vz, p.w};
+    for (const void* q : ptrs) aligned = aligned && ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+    const int64_t items = aligned ? (p.n + pnm::Vec<T>::N - 1) / pnm::Vec<T>::N : p.n;
+    const int grid = grid_for(items, 256, 8);
+#define PNM_LAUNCH(ACC, VL)                                                                          \
+    do {                                                                                             \
+        auto kern = pnm::k_project_bin<T, FUSED, ACC, VL>;                                           \
+        if (smem > 48 * 1024)                                                                        \
+            PNM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, 256, smem, st>>>(p);                                                            \
+    } while (0)
+    if (acc_mode == PNM_ACC_F64) { if (aligned) PNM_LAUNCH(PNM_ACC_F64, true); else PNM_LAUNCH(PNM_ACC_F64, false); }
+    else { if (aligned) PNM_LAUNCH(PNM_ACC_FIXED, true); else PNM_LAUNCH(PNM_ACC_FIXED, false); }
+#undef PNM_LAUNCH
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dtype,
+               const void* x, const void* y, const void* z, const void* vx, const void* vy, const void* vz,
+               const void* w, const uint8_t* mask, int mask_mode, const float* mats_host, int nchain, int nviews,
+               int sums, int acc_mode, const double* scales3_host, void* acc_maps, void* acc_cube, void* stream) {
+    if (!g) return fail(PNM_EINVAL, "%s: grid is null", who);
+    if (n < 0) return fail(PNM_EINVAL, "%s: n < 0", who);
+    if (dtype != PNM_F32 && dtype != PNM_F64) return fail(PNM_EDTYPE, "%s: dtype %d", who, dtype);
+    if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "%s: acc_mode %d", who, acc_mode);
+    if (acc_mode == PNM_ACC_FIXED && !scales3_host) return fail(PNM_EINVAL, "%s: FIXED mode needs scales", who);
+    const int map_sums = sums & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2);
+    if (!(sums & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2 | PNM_SUM_CUBE))) return fail(PNM_EINVAL, "%s: no sums requested", who);
+    if (map_sums && !acc_maps) return fail(PNM_EINVAL, "%s: acc_maps is null", who);
+    if ((sums & PNM_SUM_CUBE) && (!acc_cube || g->nv < 1)) return fail(PNM_EINVAL, "%s: cube requested without cube accumulator / V axis", who);
+    if ((sums & PNM_W_FROM_CUBE) && !((sums & PNM_SUM_CUBE) && (sums & PNM_SUM_W)))
+        return fail(PNM_EINVAL, "%s: PNM_W_FROM_CUBE needs PNM_SUM_W|PNM_SUM_CUBE", who);
+    if (mask_mode != PNM_MASK_NONE && !mask) return fail(PNM_EINVAL, "%s: mask_mode without mask", who);
+    if (mask_mode < 0 || mask_mode > 2) return fail(PNM_EINVAL, "%s: mask_mode %d", who, mask_mode);
+    if (fused) {
+        if (nchain < 1 || nchain > PNM_MAX_CHAIN) return fail(PNM_ELIMIT, "%s: nchain %d not in 1..%d", who, nchain, PNM_MAX_CHAIN);
+        if (nviews < 1 || nviews > PNM_MAX_VIEWS) return fail(PNM_ELIMIT, "%s: nviews %d not in 1..%d", who, nviews, PNM_MAX_VIEWS);
+        if (nchain * nviews > pnm::kMaxMats) return fail(PNM_ELIMIT, "%s: nchain*nviews > %d", who, pnm::kMaxMats);
+        if (!mats_host) return fail(PNM_EINVAL, "%s: mats is null", who);
+    }
+    if (n == 0) return PNM_OK;
+    if (!x || !y || !vx || (fused && (!z || !vy || !vz))) return fail(PNM_EINVAL, "%s: null particle array", who);
+
+    pnm::BinParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.x = x; p.y = y; p.z = z; p.vx = vx; p.vy = vy; p.vz = vz; p.w = w;
+    p.mask = mask; p.mask_mode = mask_mode;
+    p.nx = g->nx; p.ny = g->ny; p.nv = g->nv;
+    const int ox = 0, oy = g->nx + 1, ov = oy + g->ny + 1;
+    if (dtype == PNM_F32) { p.thr_x = g->thr32 + ox; p.thr_y = g->thr32 + oy; p.thr_v = g->thr32 + ov; }
+    else { p.thr_x = g->thr64 + ox; p.thr_y = g->thr64 + oy; p.thr_v = g->thr64 + ov; }
+    p.x0 = g->x0; p.inv_dx = g->inv_dx; p.y0 = g->y0; p.inv_dy = g->inv_dy; p.v0 = g->v0; p.inv_dv = g->inv_dv;
+    p.sums = sums; p.nchain = fused ? nchain : 1; p.nviews = fused ? nviews : 1;
+    for (int k = 0; k < 3; ++k) p.scale[k] = (acc_mode == PNM_ACC_FIXED) ? scales3_host[k] : 1.0;
+    p.acc_maps = acc_maps; p.acc_cube = acc_cube;
+    p.maps_stride = pnm_maps_acc_elems(g); p.cube_stride = pnm_cube_acc_elems(g);
+    if (fused) memcpy(p.mats, mats_host, sizeof(float) * 9 * nchain * nviews);
+
+    cudaStream_t st = as_stream(stream);
+    if (dtype == PNM_F32) return fused ? launch_bin<float, true>(p, acc_mode, st) : launch_bin<float, false>(p, acc_mode, st);
+    return fused ? launch_bin<double, true>(p, acc_mode, st) : launch_bin<double, false>(p, acc_mode, st);
+}
+
+}  // namespace
+
+extern "C" {
+
+int pnm_project_bin(const pnm_grid* g, int64_t n, int dtype, const void* x, const void* y, const void* z,
+                    const void* vx, const void* vy, const void* vz, const void* w, const uint8_t* mask,
+                    int mask_mode, const float* mats_host, int nchain, int nviews, int sums, int acc_mode,
+                    const double* scales3_host, void* acc_maps, void* acc_cube, void* stream) {
+    return bin_common("pnm_project_bin", true, g, n, dtype, x, y, z, vx, vy, vz, w, mask, mask_mode, mats_host,
+                      nchain, nviews, sums, acc_mode, scales3_host, acc_maps, acc_cube, stream);
+}
+
+int pnm_bin_points(const pnm_grid* g, int64_t n, int dtype, const void* x, const void* y, const void* d,
+                   const void* w, const uint8_t* mask, int mask_mode, int sums, int acc_mode,
+                   const double* scales3_host, void* acc_maps, void* acc_cube, void* stream) {
+    return bin_common("pnm_bin_points", false, g, n, dtype, x, y, nullptr, d, nullptr, nullptr, w, mask, mask_mode,
+                      nullptr, 1, 1, sums, acc_mode, scales3_host, acc_maps, acc_cube, stream);
+}
+
+// ------------------------------------------------------------------------------------ finalise
+int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_cube, int sums, int acc_mode,
+                       const double* scales3_host, double* M, double* V, double* S, double* S1, double* S2,
+                       void* stream) {
+    if (!g || !acc_maps) return fail(PNM_EINVAL, "pnm_finalize_vmaps: null grid / accumulator");
+    const int wfc = (sums & PNM_W_FROM_CUBE) ? 1 : 0;
+    if (wfc && !acc_cube) return fail(PNM_EINVAL, "pnm_finalize_vmaps: PNM_W_FROM_CUBE without cube");
+    const int npix = g->nx * g->ny;
+    const int grid = (npix + 255) / 256;
+    if (acc_mode == PNM_ACC_F64) {
+        pnm::k_finalize_vmaps<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, acc_cube, g->nx, g->ny, g->nv,
+                                                                              wfc, 1.0, 1.0, 1.0, M, V, S, S1, S2);
+    } else if (acc_mode == PNM_ACC_FIXED) {
+        if (!scales3_host) return fail(PNM_EINVAL, "pnm_finalize_vmaps: FIXED mode needs scales");
+        pnm::k_finalize_vmaps<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(
+            acc_maps, acc_cube, g->nx, g->ny, g->nv, wfc, 1.0 / scales3_host[0], 1.0 / scales3_host[1],
+            1.0 / scales3_host[2], M, V, S, S1, S2);
+    } else {
+        return fail(PNM_EINVAL, "pnm_finalize_vmaps: acc_mode %d", acc_mode);
+    }
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_finalize_map(const pnm_grid* g, const void* acc_maps, int acc_mode, const double* scales3_host,
+                     double* W, double* D, double* DW, void* stream) {
+    if (!g || !acc_maps) return fail(PNM_EINVAL, "pnm_finalize_map: null grid / accumulator");
+    const int npix = g->nx * g->ny;
+    const int grid = (npix + 255) / 256;
+    if (acc_mode == PNM_ACC_F64) {
+        pnm::k_finalize_map<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, npix, 1.0, 1.0, W, D, DW);
+    } else if (acc_mode == PNM_ACC_FIXED) {
+        if (!scales3_host) return fail(PNM_EINVAL, "pnm_finalize_map: FIXED mode needs scales");
+        pnm::k_finalize_map<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, npix, 1.0 / scales3_host[0],
+                                                                              1.0 / scales3_host[1], W, D, DW);
+    } else {
+        return fail(PNM_EINVAL, "pnm_finalize_map: acc_mode %d", acc_mode);
+    }
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int acc_mode, double scale_w, double* cube_out,
+                      void* stream) {
+    if (!g || !acc_cube || !cube_out) return fail(PNM_EINVAL, "pnm_finalize_cube: null argument");
+    const int64_t n = pnm_cube_acc_elems(g);
+    if (acc_mode == PNM_ACC_F64) {
+        if (cube_out != acc_cube)
+            PNM_CUDA(cudaMemcpyAsync(cube_out, acc_cube, n * sizeof(double), cudaMemcpyDeviceToDevice, as_stream(stream)));
+        return PNM_OK;
+    }
+    if (acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_finalize_cube: acc_mode %d", acc_mode);
+    pnm::k_fixed_to_f64<<<grid_for(n, 256, 16), 256, 0, as_stream(stream)>>>((const long long*)acc_cube, cube_out, n,
+                                                                           1.0 / scale_w);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+// ------------------------------------------------------------------------------------ smoothing
+int pnm_smooth_cube(const double* cube_in, double* cube_out, double* work, int32_t nx, int32_t ny, int32_t nv,
+                    const double* taps0_host, int32_t ntaps0, const double* taps1_host, int32_t ntaps1,
+                    void* stream) {
+    if (!cube_in || !cube_out || !work || !taps0_host || !taps1_host) return fail(PNM_EINVAL, "pnm_smooth_cube: null argument");
+    if (cube_in == cube_out || work == cube_in || work == cube_out) return fail(PNM_EINVAL, "pnm_smooth_cube: buffers must be distinct");
+    if (nx < 1 || ny < 1 || nv < 1) return fail(PNM_EINVAL, "pnm_smooth_cube: bad shape");
+    if (ntaps0 < 1 || ntaps1 < 1 || !(ntaps0 & 1) || !(ntaps1 & 1)) return fail(PNM_EINVAL, "pnm_smooth_cube: tap counts must be odd");
+    if (ntaps0 > PNM_MAX_TAPS || ntaps1 > PNM_MAX_TAPS) return fail(PNM_ELIMIT, "pnm_smooth_cube: more than %d taps", PNM_MAX_TAPS);
+    pnm::Taps t0, t1;
+    memset(&t0, 0, sizeof(t0)); memset(&t1, 0, sizeof(t1));
+    t0.n = ntaps0; memcpy(t0.t, taps0_host, sizeof(double) * ntaps0);
+    t1.n = ntaps1; memcpy(t1.t, taps1_host, sizeof(double) * ntaps1);
+    const int64_t total = (int64_t)nx * ny * nv;
+    const int grid = grid_for(total, 256, 8);
+    pnm::k_smooth_axis<0><<<grid, 256, 0, as_stream(stream)>>>(cube_in, work, nx, ny, nv, t0);
+    pnm::k_smooth_axis<1><<<grid, 256, 0, as_stream(stream)>>>(work, cube_out, nx, ny, nv, t1);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv, const double* binv_dev,
+                     double empty_m2, double* mom0, double* mom1, double* mom2, void* stream) {
+    if (!cube || !binv_dev || !mom0 || !mom1 || !mom2) return fail(PNM_EINVAL, "pnm_cube_moments: null argument");
+    const int nspax = nx * ny;
+    const int grid = (nspax * 32 + 255) / 256;
+    pnm::k_cube_moments<<<grid, 256, 0, as_stream(stream)>>>(cube, nspax, nv, binv_dev, empty_m2, mom0, mom1, mom2);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream) {
+    if (!out_dev || n < 0 || (n > 0 && !a)) return fail(PNM_EINVAL, "pnm_absmax: bad argument");
+    PNM_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), as_stream(stream)));
+    if (n == 0) return PNM_OK;
+    const int grid = grid_for(n, 256, 8);
+    if (dtype == PNM_F32) pnm::k_absmax<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)a, n, (unsigned long long*)out_dev);
+    else if (dtype == PNM_F64) pnm::k_absmax<double><<<grid, 256, 0, as_stream(stream)>>>((const double*)a, n, (unsigned long long*)out_dev);
+    else return fail(PNM_EDTYPE, "pnm_absmax: dtype %d", dtype);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// pnm_post.cuh -- everything after the scatter: finalisation (K5), smoothing (K4), cube moments (f1),
+// plus the materialising rotation (K1) and the abs-max reduction used to size fixed-point scales.
+#pragma once
+#include "pnm_common.cuh"
+
+namespace pnm {
+
+// ---------------------------------------------------------------- K1: materialising rotation
+struct Mat9 { float m[9]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_rotate(const T* __restrict__ x, const T* __restrict__ y,
+                                                const T* __restrict__ z, T* ox, T* oy, T* oz,
+                                                int64_t n, const __grid_constant__ Mat9 mat) {
+    const float* m = mat.m;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const T a = x[i], b = y[i], c = z[i];      // read all three before writing: in-place is allowed
+        const T r0 = rot_row(m[0], m[1], m[2], a, b, c);
+        const T r1 = rot_row(m[3], m[4], m[5], a, b, c);
+        const T r2 = rot_row(m[6], m[7], m[8], a, b, c);
+        ox[i] = r0; oy[i] = r1; oz[i] = r2;
+    }
+}
+
+// ---------------------------------------------------------------- accumulator -> float64
+template <int ACC>
+__device__ __forceinline__ double acc_load(const void* base, int64_t idx, double inv_scale) {
+    if (ACC == PNM_ACC_F64) return reinterpret_cast<const double*>(base)[idx];
+    return __dmul_rn((double)reinterpret_cast<const long long*>(base)[idx], inv_scale);
+}
+
+// K5 (grid.py:133-138).  Separate roundings (no FMA contraction) so that equal sums give
+// bit-equal V and S: numpy evaluates s2/s0, V*V and the subtraction as three ufunc calls.
+template <int ACC>
+__global__ void __launch_bounds__(256) k_finalize_vmaps(const void* acc_maps, const void* acc_cube,
+                                                        int nx, int ny, int nv, int w_from_cube,
+                                                        double is0, double is1, double is2,
+                                                        double* M, double* V, double* S, double* S1o, double* S2o) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;   // = iy*nx + ix
+    if (pix >= nx * ny) return;
+    double s0;
+    if (w_from_cube) {
+        // sum w = particles outside the V range (slot 0) + the V-sum of the cube at [ix][iy][:]
+        const int iy = pix / nx, ix = pix - iy * nx;
+        const int64_t base = ((int64_t)ix * ny + iy) * nv;
+        if (ACC == PNM_ACC_F64) {
+            double t = reinterpret_cast<const double*>(acc_maps)[(int64_t)pix * PNM_MAP_SLOTS];
+            for (int k = 0; k < nv; ++k) t = __dadd_rn(t, reinterpret_cast<const double*>(acc_cube)[base + k]);
+            s0 = t;
+        } else {
+            long long t = reinterpret_cast<const long long*>(acc_maps)[(int64_t)pix * PNM_MAP_SLOTS];
+            for (int k = 0; k < nv; ++k) t += reinterpret_cast<const long long*>(acc_cube)[base + k];
+            s0 = __dmul_rn((double)t, is0);
+        }
+    } else {
+        s0 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 0, is0);
+    }
+    const double s1 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 1, is1);
+    const double s2 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 2, is2);
+    double v = 0.0, s = 0.0;
+    if (s0 != 0.0) {
+        v = __ddiv_rn(s1, s0);
+        s = __dsqrt_rn(__dsub_rn(__ddiv_rn(s2, s0), __dmul_rn(v, v)));
+    }
+    if (M) M[pix] = s0;
+    if (V) V[pix] = v;
+    if (S) S[pix] = s;
+    if (S1o) S1o[pix] = s1;
+    if (S2o) S2o[pix] = s2;
+}
+
+// grid.py:203-205
+template <int ACC>
+__global__ void __launch_bounds__(256) k_finalize_map(const void* acc_maps, int npix, double is0, double is1,
+                                                      double* W, double* D, double* DW) {
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= npix) return;
+    const double s0 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 0, is0);
+    const double s1 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 1, is1);
+    if (W) W[pix] = s0;
+    if (D) D[pix] = (s0 != 0.0) ? __ddiv_rn(s1, s0) : 0.0;
+    if (DW) DW[pix] = s1;
+}
+
+__global__ void __launch_bounds__(256) k_fixed_to_f64(const long long* in, double* out, int64_t n, double inv_scale) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __dmul_rn((double)in[i], inv_scale);
+}
+
+// ---------------------------------------------------------------- K4: separable Gaussian
+// cube [nx][ny][nv], iv contiguous.  One pass convolves along AXIS (0 or 1) with zero fill:
+//   out[i] = sum_t taps[t] * in[i + (t - r) * stride_axis]
+// Threads run along iv so every tap is a coalesced row read served by L2 (the cube is resident).
+struct Taps { double t[PNM_MAX_TAPS]; int n; };
+
+template <int AXIS>
+__global__ void __launch_bounds__(256) k_smooth_axis(const double* __restrict__ in, double* __restrict__ out,
+                                                     int nx, int ny, int nv, const __grid_constant__ Taps taps) {
+    const int64_t total = (int64_t)nx * ny * nv;
+    const int r = taps.n / 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int64_t plane = i / nv;                  // ix*ny + iy
+        const int ix = (int)(plane / ny), iy = (int)(plane - (int64_t)ix * ny);
+        const int pos = AXIS == 0 ? ix : iy;
+        const int len = AXIS == 0 ? nx : ny;
+        const int64_t step = AXIS == 0 ? (int64_t)ny * nv : (int64_t)nv;
+        const int lo = max(0, r - pos), hi = min(taps.n - 1, r + (len - 1 - pos));
+        double acc = 0.0;
+        for (int t = lo; t <= hi; ++t) acc = __fma_rn(taps.t[t], in[i + (int64_t)(t - r) * step], acc);
+        out[i] = acc;
+    }
+}
+
+// ---------------------------------------------------------------- f1: per-spaxel LOSVD moments
+// losvd.py:41-51 + misc_functions.py:70-90: one warp per spaxel, shuffle reduction over iv.
+// An all-zero LOSVD gives (0, 0, min(diff(binv))/3) (misc_functions.py:81-84) = empty_m2.
+__global__ void __launch_bounds__(256) k_cube_moments(const double* __restrict__ cube, int nspax, int nv,
+                                                      const double* __restrict__ binv, double empty_m2,
+                                                      double* mom0, double* mom1, double* mom2) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nspax) return;
+    const double* c = cube + (int64_t)warp * nv;
+    double a0 = 0, a1 = 0, a2 = 0;
+    bool any = false;
+    for (int k = lane; k < nv; k += 32) {
+        const double v = binv[k], f = c[k];
+        any = any || (f != 0.0);
+        a0 += f; a1 += v * f; a2 += v * v * f;
+    }
+    any = __any_sync(0xffffffffu, any);
+    for (int o = 16; o; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (lane == 0) {
+        double m0 = 0, m1 = 0, m2 = empty_m2;
+        if (any) { m0 = a0; m1 = a1 / a0; m2 = sqrt(a2 / a0 - m1 * m1); }
+        mom0[warp] = m0; mom1[warp] = m1; mom2[warp] = m2;
+    }
+}
+
+// ---------------------------------------------------------------- abs-max (fixed-point scale)
+// Non-negative doubles order like their bit patterns, so one integer atomicMax per block suffices.
+template <typename T>
+__global__ void __launch_bounds__(256) k_absmax(const T* __restrict__ a, int64_t n, unsigned long long* out) {
+    double m = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = fabs((double)a[i]);
+        if (v > m && is_finite(v)) m = v;
+    }
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    __shared__ double sm[8];
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) m = fmax(m, sm[k]);
+        atomicMax(out, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+}  // namespace pnm

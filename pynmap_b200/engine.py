@@ -1,0 +1,310 @@
+"""Device engine behind the pynmap call surface: grids, accumulators and the calls into
+libpnm_b200.so.  torch is used for device memory, streams and (in sharded.py) the
+process group only -- every arithmetic step of the path is a kernel of the library.
+
+Layout in HBM
+  particles     SoA, one contiguous array per coordinate (x, y, z, vx, vy, vz, w)
+  maps acc      [view][iy][ix][4]  8-byte slots {S0 = sum w, S1 = sum w d, S2 = sum w d^2, -}
+  cube acc      [view][ix][iy][iv] 8-byte elements (sum w)
+  outputs       float64: maps (nY, nX) like grid.py:126-131 after .T, cube (nX, nY, nV) like grid.py:259
+"""
+import ctypes
+import math
+import threading
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_TORCH_TO_PNM = {torch.float32: _lib.F32, torch.float64: _lib.F64}
+
+
+# ----------------------------------------------------------------------------- small helpers
+def is_cuda_tensor(a):
+    return isinstance(a, torch.Tensor) and a.is_cuda
+
+
+def current_device():
+    _lib.require_device()
+    if not torch.cuda.is_available():
+        raise _lib.PnmError("torch sees no CUDA device: pynmap_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def result_dtype(*arrays):
+    """np.result_type(float32, inputs...) restricted to the two dtypes the kernels are
+    compiled for: the reference's rotation matrix is float32 (rotation.py:107-108), so
+    float32 data stay float32 and anything wider (or integer) becomes float64."""
+    dts = []
+    for a in arrays:
+        if a is None:
+            continue
+        if isinstance(a, torch.Tensor):
+            dts.append(torch.empty(0, dtype=a.dtype).numpy().dtype if a.dtype != torch.bfloat16 else np.dtype(np.float32))
+        else:
+            dts.append(np.asarray(a).dtype)
+    dt = np.result_type(np.float32, *dts)
+    return torch.float32 if dt == np.float32 else torch.float64
+
+
+def to_device(a, dtype, device=None):
+    """1-D contiguous device tensor of `dtype` from numpy / torch input (copy only if needed)."""
+    if a is None:
+        return None
+    device = device or current_device()
+    if isinstance(a, torch.Tensor):
+        t = a.detach()
+    else:
+        arr = np.asarray(a)
+        if arr.dtype == np.bool_:
+            arr = arr.astype(np.uint8)
+        t = torch.from_numpy(np.ascontiguousarray(arr))
+    t = t.to(device=device, dtype=dtype, non_blocking=True)
+    return t.contiguous()
+
+
+def to_output(t, want_torch):
+    return t if want_torch else t.cpu().numpy()
+
+
+# ----------------------------------------------------------------------------- bin edges
+def expand_nxy(nXY):
+    """grid.py:103-107 -- scalar nXY means a square grid; only 1 or 2 entries are legal."""
+    if np.size(nXY) == 1:
+        n = int(np.asarray(nXY).reshape(-1)[0])
+        return n, n
+    if np.size(nXY) != 2:
+        return None
+    return int(nXY[0]), int(nXY[1])
+
+
+def bin_edges(lo, hi, n):
+    """grid.py:119-124: edges padded by half a pixel so that centres are linspace(lo, hi, n).
+    Built with the reference's numpy expression on the host: np.linspace edges are not
+    exactly uniform, and the kernel compares against these very doubles."""
+    half = (hi - lo) / (n - 1) / 2.
+    return np.linspace(lo - half, hi + half, n + 1)
+
+
+class Grid(object):
+    """Edge tables for one (limXY, nXY[, limV, nV]) on one device (pnm_grid handle)."""
+
+    def __init__(self, limXY, nx, ny, limV=None, nv=0, device=None):
+        self.device = device or current_device()
+        self.nx, self.ny, self.nv = int(nx), int(ny), int(nv)
+        self.limXY = [float(v) for v in limXY]
+        self.limV = None if limV is None else [float(v) for v in limV]
+        self.edges_x = bin_edges(limXY[0], limXY[1], self.nx)
+        self.edges_y = bin_edges(limXY[2], limXY[3], self.ny)
+        self.edges_v = bin_edges(limV[0], limV[1], self.nv) if self.nv else None
+        self.handle = ctypes.c_void_p()
+        ex, ey = _lib.doubles(self.edges_x), _lib.doubles(self.edges_y)
+        ev = _lib.doubles(self.edges_v) if self.nv else None
+        with torch.cuda.device(self.device):
+            _lib.call("pnm_grid_create", self.nx, ex, self.ny, ey, self.nv, ev, ctypes.byref(self.handle))
+
+    @property
+    def maps_elems(self):
+        return self.nx * self.ny * _lib.MAP_SLOTS
+
+    @property
+    def cube_elems(self):
+        return self.nx * self.ny * self.nv
+
+    def centres(self):
+        px = np.linspace(self.limXY[0], self.limXY[1], self.nx)
+        py = np.linspace(self.limXY[2], self.limXY[3], self.ny)
+        pv = np.linspace(self.limV[0], self.limV[1], self.nv) if self.nv else None
+        return px, py, pv
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().pnm_grid_destroy(self.handle)
+        except Exception:
+            pass
+
+
+_GRID_CACHE = OrderedDict()
+_GRID_LOCK = threading.Lock()
+_GRID_CACHE_MAX = 32
+
+
+def get_grid(limXY, nx, ny, limV=None, nv=0, device=None):
+    device = device or current_device()
+    key = (str(device), tuple(float(v) for v in limXY), int(nx), int(ny),
+           None if limV is None or not nv else tuple(float(v) for v in limV), int(nv))
+    with _GRID_LOCK:
+        g = _GRID_CACHE.get(key)
+        if g is None:
+            g = Grid(limXY, nx, ny, limV if nv else None, nv, device)
+            _GRID_CACHE[key] = g
+            while len(_GRID_CACHE) > _GRID_CACHE_MAX:
+                _GRID_CACHE.popitem(last=False)
+        else:
+            _GRID_CACHE.move_to_end(key)
+    return g
+
+
+# ----------------------------------------------------------------------------- accumulate mode
+class AccMode(object):
+    """'f64' (default): float64 reduction atomics.  'fixed': int64 fixed point, deterministic."""
+
+    def __init__(self, name="f64"):
+        name = {"float64": "f64", "int64": "fixed", "fixed64": "fixed"}.get(str(name), str(name))
+        if name not in ("f64", "fixed"):
+            raise ValueError("accumulate must be 'f64' or 'fixed', got %r" % (name,))
+        self.name = name
+        self.code = _lib.ACC_F64 if name == "f64" else _lib.ACC_FIXED
+        self.dtype = torch.float64 if name == "f64" else torch.int64
+
+
+def fixed_scales(n_total, max_w, max_d):
+    """Power-of-two scales for (w, w*d, w*d*d) such that n_total worst-case terms cannot
+    overflow int64: n * max|term| * 2^k <= 2^62.  Exactly representable, so `value*scale`
+    is exact and only the final rint rounds."""
+    out = []
+    for bound in (max_w, max_w * max_d, max_w * max_d * max_d):
+        bound = max(float(bound), 1e-300) * max(int(n_total), 1)
+        k = int(math.floor(62 - math.log2(bound)))
+        k = max(-1000, min(k, 1000))
+        out.append(math.ldexp(1.0, k))
+    return out
+
+
+def absmax(t):
+    """max |t| over finite entries as a python float (one small sync)."""
+    if t is None or t.numel() == 0:
+        return 0.0
+    out = torch.empty(1, dtype=torch.float64, device=t.device)
+    _lib.call("pnm_absmax", ptr(t), t.numel(), _TORCH_TO_PNM[t.dtype], ptr(out), stream_ptr())
+    return float(out.item())
+
+
+# ----------------------------------------------------------------------------- the scatter
+def new_accumulators(grid, sums, acc, nviews=1):
+    maps = cube = None
+    if sums & (_lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2):
+        maps = torch.zeros(nviews * grid.maps_elems, dtype=acc.dtype, device=grid.device)
+    if sums & _lib.SUM_CUBE:
+        cube = torch.zeros(nviews * grid.cube_elems, dtype=acc.dtype, device=grid.device)
+    return maps, cube
+
+
+def _scales_arg(acc, scales):
+    if acc.code == _lib.ACC_FIXED:
+        if scales is None:
+            raise ValueError("fixed-point accumulation needs scales")
+        return _lib.doubles(scales)
+    return None
+
+
+def project_bin(grid, soa, w, mats, nchain, nviews, sums, acc, scales, maps, cube, mask=None, mask_mode=0):
+    """pnm_project_bin: soa = (x, y, z, vx, vy, vz) device tensors of one dtype."""
+    x = soa[0]
+    mats = np.ascontiguousarray(np.asarray(mats, dtype=np.float32).reshape(-1))
+    assert mats.size == 9 * nchain * nviews
+    _lib.call("pnm_project_bin", grid.handle, x.numel(), _TORCH_TO_PNM[x.dtype],
+              ptr(soa[0]), ptr(soa[1]), ptr(soa[2]), ptr(soa[3]), ptr(soa[4]), ptr(soa[5]),
+              ptr(w), ptr(mask), mask_mode,
+              mats.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), nchain, nviews,
+              sums, acc.code, _scales_arg(acc, scales), ptr(maps), ptr(cube), stream_ptr())
+
+
+def bin_points(grid, x, y, d, w, sums, acc, scales, maps, cube, mask=None, mask_mode=0):
+    """pnm_bin_points: already projected coordinates."""
+    _lib.call("pnm_bin_points", grid.handle, x.numel(), _TORCH_TO_PNM[x.dtype],
+              ptr(x), ptr(y), ptr(d), ptr(w), ptr(mask), mask_mode,
+              sums, acc.code, _scales_arg(acc, scales), ptr(maps), ptr(cube), stream_ptr())
+
+
+def finalize_vmaps(grid, maps, cube, sums, acc, scales, want_raw=False):
+    """-> M, V, S (and S1, S2 when want_raw) as float64 (nY, nX) device tensors."""
+    shape = (grid.ny, grid.nx)
+    M, V, S = (torch.empty(shape, dtype=torch.float64, device=grid.device) for _ in range(3))
+    S1 = S2 = None
+    if want_raw:
+        S1, S2 = (torch.empty(shape, dtype=torch.float64, device=grid.device) for _ in range(2))
+    _lib.call("pnm_finalize_vmaps", grid.handle, ptr(maps), ptr(cube), sums, acc.code, _scales_arg(acc, scales),
+              ptr(M), ptr(V), ptr(S), ptr(S1), ptr(S2), stream_ptr())
+    return (M, V, S, S1, S2) if want_raw else (M, V, S)
+
+
+def finalize_map(grid, maps, acc, scales):
+    shape = (grid.ny, grid.nx)
+    W, D, DW = (torch.empty(shape, dtype=torch.float64, device=grid.device) for _ in range(3))
+    _lib.call("pnm_finalize_map", grid.handle, ptr(maps), acc.code, _scales_arg(acc, scales),
+              ptr(W), ptr(D), ptr(DW), stream_ptr())
+    return W, D, DW
+
+
+def finalize_cube(grid, cube, acc, scales):
+    """-> float64 (nX, nY, nV) device tensor (a view of the accumulator in f64 mode)."""
+    shape = (grid.nx, grid.ny, grid.nv)
+    if acc.code == _lib.ACC_F64:
+        return cube.view(shape)
+    out = torch.empty(shape, dtype=torch.float64, device=grid.device)
+    _lib.call("pnm_finalize_cube", grid.handle, ptr(cube), acc.code, float(scales[0]), ptr(out), stream_ptr())
+    return out
+
+
+# ----------------------------------------------------------------------------- smoothing
+FWHM_TO_SIGMA = 1.0 / (2.0 * math.sqrt(2.0 * math.log(2.0)))   # astropy.stats.gaussian_fwhm_to_sigma
+
+
+def gaussian_support(sig_a, sig_b):
+    """astropy Gaussian2DKernel default size: ceil(8 * max sigma) bumped to odd."""
+    s = int(math.ceil(8 * max(sig_a, sig_b)))
+    return s + 1 - s % 2
+
+
+def gaussian_taps(sigma_pix, support):
+    """Normalised 1-D factor of the (separable) truncated 2-D Gaussian, float64 on the host."""
+    half = (support - 1) // 2
+    i = np.arange(-half, half + 1, dtype=np.float64)
+    g = np.exp(-0.5 * (i / sigma_pix) ** 2)
+    return g / g.sum()
+
+
+def smooth_cube(cube, taps_axis0, taps_axis1):
+    """pnm_smooth_cube on a float64 (nX, nY, nV) device tensor -> new tensor."""
+    cube = cube.contiguous()
+    nx, ny, nv = cube.shape
+    out = torch.empty_like(cube)
+    work = torch.empty_like(cube)
+    t0, t1 = _lib.doubles(taps_axis0), _lib.doubles(taps_axis1)
+    _lib.call("pnm_smooth_cube", ptr(cube), ptr(out), ptr(work), nx, ny, nv, t0, len(taps_axis0), t1,
+              len(taps_axis1), stream_ptr())
+    return out
+
+
+def cube_moments(cube, binv):
+    cube = cube.contiguous()
+    nx, ny, nv = cube.shape
+    binv = np.asarray(binv, dtype=np.float64)
+    bv = to_device(binv, torch.float64, cube.device)
+    empty_m2 = float(np.min(np.diff(binv)) / 3.0)        # misc_functions.py:81-84
+    m0, m1, m2 = (torch.empty((nx, ny), dtype=torch.float64, device=cube.device) for _ in range(3))
+    _lib.call("pnm_cube_moments", ptr(cube), nx, ny, nv, ptr(bv), empty_m2, ptr(m0), ptr(m1), ptr(m2), stream_ptr())
+    return m0, m1, m2
+
+
+def rotate_soa(soa3, mat, out=None):
+    """pnm_rotate on three SoA tensors -> three new tensors (rows of a (3, N) tensor)."""
+    x, y, z = soa3
+    if out is None:
+        out = torch.empty((3, x.numel()), dtype=x.dtype, device=x.device)
+    m = np.ascontiguousarray(np.asarray(mat, dtype=np.float32).reshape(9))
+    _lib.call("pnm_rotate", ptr(x), ptr(y), ptr(z), ptr(out[0]), ptr(out[1]), ptr(out[2]), x.numel(),
+              _TORCH_TO_PNM[x.dtype], m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), stream_ptr())
+    return out

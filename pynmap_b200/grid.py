@@ -1,0 +1,116 @@
+"""Gridding layer with the reference's signatures (pynmap/grid.py:70-262):
+``points_2vmaps``, ``points_2map``, ``points_2losvds``.  Bodies run on the GPU through
+libpnm_b200 (pnm_bin_points + pnm_finalize_*); numpy in -> numpy out, CUDA tensors in ->
+CUDA tensors out.  The extra keyword ``accumulate`` ('f64' default, 'fixed' = int64
+fixed point) is the only addition to the reference's call surface.
+"""
+import numpy as np
+import torch
+
+from . import _lib, engine
+from .losvd import LOSVD
+
+
+def _prepare(arrays, mask):
+    """Common dtype (np.result_type like the reference's `wm * vm`, grid.py:128) and device copies."""
+    want_torch = any(engine.is_cuda_tensor(a) for a in arrays if a is not None)
+    dtype = engine.result_dtype(*arrays)
+    n = None
+    dev = []
+    for a in arrays:
+        t = engine.to_device(a, dtype) if a is not None else None
+        if t is not None:
+            t = t.reshape(-1)
+            if n is None:
+                n = t.numel()
+            elif t.numel() != n:
+                raise ValueError("operands could not be broadcast together: lengths %d and %d" % (n, t.numel()))
+        dev.append(t)
+    m = None
+    if mask is not None:
+        m = engine.to_device(mask, torch.uint8).reshape(-1)
+        if m.numel() != n:
+            raise IndexError("boolean index did not match indexed array: mask has %d entries for %d points"
+                             % (m.numel(), n))
+    return dev, m, want_torch, dtype
+
+
+def _scales_for(acc, n, w, d):
+    if acc.code != _lib.ACC_FIXED:
+        return None
+    return engine.fixed_scales(n, engine.absmax(w) if w is not None else 1.0, engine.absmax(d))
+
+
+def _mesh(grid, want_torch):
+    px, py, _ = grid.centres()
+    gx, gy = np.meshgrid(px, py)
+    if want_torch:
+        return torch.from_numpy(gx).to(grid.device), torch.from_numpy(gy).to(grid.device)
+    return gx, gy
+
+
+def points_2vmaps(x, y, v, weights=None, limXY=[-1, 1, -1, 1], nXY=11, mask=None, accumulate="f64"):
+    """First two velocity moments on a grid (pynmap/grid.py:70-143).
+
+    Returns gridX, gridY, M, V, S, all (nY, nX) float64.  Quirk kept from the reference: a
+    mask entry only removes a particle whose ``v`` is also non-finite (grid.py:113-115)."""
+    n2 = engine.expand_nxy(nXY)
+    if n2 is None:
+        print("ERROR: dimension of n should be 1 or 2")
+        return 0, 0, 0, 0, 0
+    (xd, yd, vd, wd), m, want_torch, _ = _prepare([x, y, v, weights], mask)
+    grid = engine.get_grid(limXY, n2[0], n2[1])
+    acc = engine.AccMode(accumulate)
+    sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2
+    scales = _scales_for(acc, xd.numel(), wd, vd)
+    maps, _ = engine.new_accumulators(grid, sums, acc)
+    engine.bin_points(grid, xd, yd, vd, wd, sums, acc, scales, maps, None, m,
+                      _lib.MASK_AND_NONFINITE if m is not None else _lib.MASK_NONE)
+    M, V, S = engine.finalize_vmaps(grid, maps, None, sums, acc, scales)
+    gx, gy = _mesh(grid, want_torch)
+    return gx, gy, engine.to_output(M, want_torch), engine.to_output(V, want_torch), engine.to_output(S, want_torch)
+
+
+def points_2map(x, y, data=None, weights=None, limXY=[-1, 1, -1, 1], nXY=10, mask=None, accumulate="f64"):
+    """Weighted mean of ``data`` on a grid (pynmap/grid.py:145-210) -> gridX, gridY, W, D, DW."""
+    n2 = engine.expand_nxy(nXY)
+    if n2 is None:
+        print("ERROR: dimension of n should be 1 or 2")
+        return 0, 0, 0, 0, 0
+    if data is None:
+        data = torch.ones_like(x) if isinstance(x, torch.Tensor) else np.ones_like(x)
+    (xd, yd, dd, wd), m, want_torch, _ = _prepare([x, y, data, weights], mask)
+    grid = engine.get_grid(limXY, n2[0], n2[1])
+    acc = engine.AccMode(accumulate)
+    sums = _lib.SUM_W | _lib.SUM_WD
+    scales = _scales_for(acc, xd.numel(), wd, dd)
+    maps, _ = engine.new_accumulators(grid, sums, acc)
+    engine.bin_points(grid, xd, yd, dd, wd, sums, acc, scales, maps, None, m,
+                      _lib.MASK_AND_NONFINITE if m is not None else _lib.MASK_NONE)
+    W, D, DW = engine.finalize_map(grid, maps, acc, scales)
+    gx, gy = _mesh(grid, want_torch)
+    return gx, gy, engine.to_output(W, want_torch), engine.to_output(D, want_torch), engine.to_output(DW, want_torch)
+
+
+def points_2losvds(x, y, data, weights=None, limXY=[-1, 1, -1, 1], nXY=10, limV=[-1000, 1000], nV=10,
+                   mask=None, accumulate="f64"):
+    """(x, y, data) weighted histogram as a LOSVD object (pynmap/grid.py:212-262).
+    The cube is indexed [ix, iy, iv] (not transposed, unlike the maps)."""
+    n2 = engine.expand_nxy(nXY)
+    if n2 is None:
+        print("ERROR: dimension of n should be 1 or 2")
+        return 0, 0, 0, 0, 0
+    (xd, yd, dd, wd), m, want_torch, _ = _prepare([x, y, data, weights], mask)
+    if m is not None and wd is not None and bool(m.any()):
+        # grid.py:251-259 masks x/y/data but not the weights: numpy then refuses the lengths
+        raise ValueError("The weights and list don't have the same length.")
+    nV = int(nV)
+    grid = engine.get_grid(limXY, n2[0], n2[1], limV, nV)
+    acc = engine.AccMode(accumulate)
+    scales = _scales_for(acc, xd.numel(), wd, None)
+    _, cube = engine.new_accumulators(grid, _lib.SUM_CUBE, acc)
+    engine.bin_points(grid, xd, yd, dd, wd, _lib.SUM_CUBE, acc, scales, None, cube, m,
+                      _lib.MASK_PLAIN if m is not None else _lib.MASK_NONE)
+    out = engine.finalize_cube(grid, cube, acc, scales)
+    px, py, pv = grid.centres()
+    return LOSVD(px, py, pv, engine.to_output(out, want_torch))

@@ -1,0 +1,489 @@
+"""User-facing object model with the reference's interface (pynmap/pynmap.py:40-474):
+``snapshot`` (read / reset / rotate / velocity_moments / create_map / create_losvds) and the
+``SnapMap`` result container.
+
+B200-native differences that do not change the call surface:
+  * particles live in HBM as SoA tensors (x, y, z, vx, vy, vz, mass/flux);
+  * ``rotate`` only records the float32 matrix; ``velocity_moments`` / ``create_map`` /
+    ``create_losvds`` run ONE fused rotate+project+bin kernel over the original arrays
+    (each compounded rotation is re-applied per particle in registers with the same
+    rounding as a materialised rotation, so the results are bit-identical);
+  * ``pos`` / ``vel`` are materialised lazily (pnm_rotate) only if the user reads them.
+Additions: ``snapshot.from_arrays`` (tensors instead of an ascii file), the ``accumulate``
+keyword ('f64' | 'fixed'), ``project`` (maps + LOSVD cube from a single read) and
+``project_views`` (many viewing angles from a single read).
+"""
+import copy
+import os
+from os.path import join as joinpath
+
+import numpy as np
+import torch
+
+from . import _lib, engine
+from .grid import points_2losvds, points_2map, points_2vmaps
+from .losvd import LOSVD
+from .rotation import rotation_matrix
+
+# Default scales and limits (pynmap/pynmap.py:31-37)
+default_scale = 1000.0
+default_Vscale = 1000.0
+default_limXY = [-default_scale, default_scale, -default_scale, default_scale]
+default_limV = [-default_Vscale, default_Vscale]
+default_npoint = 100
+default_nVpoint = 100
+
+
+def convert_to_list(a):
+    """pynmap/misc_io.py:359-368: a scalar angle becomes ``[np.float32(a)]`` -- which is why
+    the rotation trigonometry of snapshot.rotate runs in float32."""
+    return [np.float32(a)]
+
+
+def read_ascii_files(filename):
+    """One particle per line: x y z Vx Vy Vz [mass age Z/H ...] (pynmap/misc_io.py:143-182)."""
+    if os.path.isfile(filename):
+        try:
+            data = np.loadtxt(filename).T
+            print("Found {} columns in file".format(data.shape[0]))
+            pos = np.vstack(data[:3]).T
+            vel = np.vstack(data[3:6]).T
+            return pos, vel, data[6:]
+        except ValueError:
+            print("ERROR: could not read content of the input file")
+    else:
+        print("Input file not found: {0}".format(filename))
+    return None, None, None
+
+
+dic_io = {"Magneticum": read_ascii_files, "ascii": read_ascii_files}
+
+
+class SnapMap(object):
+    """Result container (pynmap/pynmap.py:40-63): attributes come from ``input_dic``."""
+
+    def __init__(self, name="", info=None, input_dic={}):
+        self._info = info
+        self.name = name
+        for item in input_dic.keys():
+            setattr(self, item, input_dic[item])
+        self.input_keys = list(input_dic.keys())
+
+    def info(self):
+        print("Name {0}: {1}".format(self.name, self._info))
+        print("List of keys: {}".format(self.input_keys))
+
+    @property
+    def extent(self):
+        if hasattr(self, 'X') & hasattr(self, 'Y'):
+            X, Y = self.X, self.Y
+            if isinstance(X, torch.Tensor):
+                return [float(X.min()), float(X.max()), float(Y.min()), float(Y.max())]
+            return [np.min(X), np.max(X), np.min(Y), np.max(Y)]
+        return None
+
+
+class snapshot(object):
+    """N-body snapshot (pynmap/pynmap.py:99-474)."""
+
+    def __init__(self, folder="", snap_name=None, snap_type="ascii", distance=10.0, MLrecipe="SSPs",
+                 inclination=0., PA=0., verbose=True, extra_labels=[], ml_function=None,
+                 output="numpy"):
+        self.verbose = verbose
+        self.distance = distance
+        self.pc_per_arcsec = self.distance * np.pi / 0.648
+        self.MLrecipe = MLrecipe
+        self.ml_function = ml_function
+        self._PA_orig = PA
+        self._inclination_orig = inclination
+        self.snap_type = snap_type
+        self.extra_labels = extra_labels
+        self.output = output
+        self._soa = None
+        self.folder = folder
+        if snap_name is None:
+            print('ERROR: no filename for the main input snapshot file provided')
+            return
+        self.snap_name = snap_name
+        in_name = joinpath(self.folder, self.snap_name)
+        if not os.path.isfile(in_name):
+            print('ERROR: filename {} does not exists'.format(in_name))
+            return
+        self.read(in_name)
+        self._reset_rotations()
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_arrays(cls, pos, vel, mass=None, age=None, MH=None, flux=None, distance=10.0,
+                    MLrecipe=None, verbose=False, ml_function=None, output=None, **extra):
+        """Build a snapshot from (N, 3) / (3, N)-SoA arrays or tensors instead of a file.
+        ``output`` = 'torch' keeps results on the GPU, 'numpy' copies them to the host
+        (default: 'torch' if ``pos`` is a CUDA tensor)."""
+        self = cls(snap_name=None, distance=distance, MLrecipe=MLrecipe, verbose=verbose,
+                   ml_function=ml_function) if False else cls.__new__(cls)
+        self.verbose = verbose
+        self.distance = distance
+        self.pc_per_arcsec = distance * np.pi / 0.648
+        self.MLrecipe = MLrecipe
+        self.ml_function = ml_function
+        self._PA_orig, self._inclination_orig = 0., 0.
+        self.snap_type, self.extra_labels = "arrays", list(extra.keys())
+        self.folder, self.snap_name = "", "<arrays>"
+        self.output = output or ("torch" if engine.is_cuda_tensor(pos) else "numpy")
+        for k, v in extra.items():
+            setattr(self, k, v)
+        self._ingest(pos, vel, mass, age, MH, flux)
+        self._reset_rotations()
+        return self
+
+    def _ingest(self, pos, vel, mass, age, MH, flux=None):
+        dtype = engine.result_dtype(pos, vel)
+        self._soa = self._as_soa(pos, dtype), self._as_soa(vel, dtype)
+        self.npart = self._soa[0].shape[1]
+        dev = self._soa[0].device
+        self.mass = engine.to_device(mass, dtype, dev) if mass is not None else torch.ones(self.npart, dtype=dtype, device=dev)
+        self.age = engine.to_device(age, dtype, dev) if age is not None else torch.zeros_like(self.mass)
+        self.MH = engine.to_device(MH, dtype, dev) if MH is not None else torch.zeros_like(self.mass)
+        if flux is not None:
+            self.flux = engine.to_device(flux, dtype, dev)
+            self.ML = None
+        else:
+            self.ML = self.compute_ml()
+        self.mask = (self.mass == 0)
+        self._absmax = {}
+        self.reset()
+
+    @staticmethod
+    def _as_soa(a, dtype):
+        """-> (3, N) contiguous device tensor; accepts (N, 3) (any memory order) or (3, N)."""
+        t = a.detach() if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
+        if t.dim() != 2 or 3 not in t.shape:
+            raise ValueError("positions / velocities must be (N, 3) or (3, N), got %s" % (tuple(t.shape),))
+        t = t.to(device=engine.current_device(), dtype=dtype)
+        if t.shape[1] == 3 and t.shape[0] != 3:
+            t = t.t()
+        elif t.shape == (3, 3):
+            t = t.t()   # ambiguous: follow the reference's (N, 3) convention
+        return t.contiguous()
+
+    def _check_attrs(self, list_attr=['']):
+        return all(hasattr(self, attr) for attr in list_attr)
+
+    def _reset_rotations(self):
+        self.PAs = []
+        self.inclinations = []
+
+    def read(self, filename):
+        """Read the input file (pynmap/pynmap.py:182-232) and upload the particles."""
+        if self.verbose:
+            print("Opening Input file {0} ".format(filename))
+            print("By default, will read all 6 positions/velocities: x, y, z, Vx, Vy, Vz")
+        pos, vel, data = dic_io[self.snap_type](filename)
+        if pos is None:
+            print("ERROR: file may be empty. \n"
+                  "       Did not succeed to read positions and velocities.\n"
+                  "       - Aborting")
+            return
+        if data.shape[0] != len(self.extra_labels):
+            print("WARNING: cannot convert data beyond positions/velocities/masses")
+        else:
+            for i, lab in enumerate(self.extra_labels):
+                setattr(self, lab, data[i])
+        mass = getattr(self, 'mass', None)
+        age = getattr(self, 'age', None)
+        if age is None and hasattr(self, 'logage'):
+            age = 10 ** (self.logage)
+        MH = getattr(self, 'MH', None)
+        if MH is None and hasattr(self, 'ZH'):
+            MH = np.log10(self.ZH) - np.log10(0.19)
+        self._ingest(pos, vel, mass, age, MH)
+
+    def compute_ml(self):
+        """flux = mass / ML (pynmap/pynmap.py:234-236).  The SSP interpolation of the reference
+        (misc_functions.compute_ml_ssps, scipy griddata on the E-MILES tables) is a host-side,
+        once-per-snapshot step outside the hot path: pass ``ml_function`` to
+        plug it in, or ``flux=`` to from_arrays.  Any other recipe is M/L = 1."""
+        if self.ml_function is not None:
+            ml = self.ml_function(self.mass, self.age, self.MH)
+            self.ML = engine.to_device(ml, self.mass.dtype, self.mass.device)
+        elif self.MLrecipe == "SSPs":
+            raise NotImplementedError(
+                "MLrecipe='SSPs' needs the reference's SSP tables: pass ml_function=pynmap.misc_functions."
+                "compute_ml_ssps (host side) or precomputed flux; use MLrecipe=None for M/L = 1")
+        else:
+            self.ML = torch.ones_like(self.mass)
+        self.flux = self.mass / self.ML
+
+    # ------------------------------------------------------------------ rotation state
+    def reset(self):
+        """Back to the original positions / velocities (pynmap/pynmap.py:238-244): drops the
+        recorded matrices; no copy is made because the originals are never overwritten."""
+        self._base = self._soa
+        self._chain = []
+        self._materialised = None
+        self._reset_rotations()
+
+    def rotate(self, PA=0., inclination=90., reset=True, direct=True):
+        """Counter-clockwise rotation of PA (around z) then inclination (around x), degrees
+        (pynmap/pynmap.py:246-285).  Recorded lazily; see the module docstring."""
+        if self._soa is None:
+            print('WARNING: no positions - Aborting rotation')
+            return
+        if reset:
+            self.reset()
+        LPA = convert_to_list(PA)
+        Linclination = convert_to_list(inclination)
+        for pa, inclin in zip(LPA, Linclination):
+            mat = rotation_matrix(pa, inclin, direct=direct)   # raises for a list of angles, like the reference
+            if len(self._chain) >= _lib.MAX_CHAIN:
+                self._rebase()
+            self._chain.append(mat)
+            self._materialised = None
+            self.PAs.append(pa)
+            self.inclinations.append(inclin)
+        if self.verbose:
+            print('Rotations done!')
+
+    def _materialise(self):
+        if self._materialised is None:
+            pos, vel = self._base
+            for mat in self._chain:
+                pos = engine.rotate_soa((pos[0], pos[1], pos[2]), mat)
+                vel = engine.rotate_soa((vel[0], vel[1], vel[2]), mat)
+            self._materialised = (pos, vel)
+        return self._materialised
+
+    def _rebase(self):
+        self._base = self._materialise()
+        self._chain = []
+
+    def _out(self, t):
+        return t if self.output == "torch" else t.cpu().numpy()
+
+    @property
+    def pos(self):
+        """(N, 3) rotated positions, column-contiguous like the reference's (rotation.py:115)."""
+        if self._soa is None:
+            return None
+        return self._out(self._materialise()[0].t())
+
+    @property
+    def vel(self):
+        if self._soa is None:
+            return None
+        return self._out(self._materialise()[1].t())
+
+    def info(self):
+        print("Input file name: {0} with type {1}".format(self.snap_name, self.snap_type))
+        print("Number of particles: {0}".format(self.npart))
+        print("Original PA={0} and inclination={1}".format(self._PA_orig, self._inclination_orig))
+        print("Applied rotations: PAs        Inclinations")
+        if len(self.PAs) > 0:
+            for k, (pa, inclin) in enumerate(zip(self.PAs, self.inclinations)):
+                print("{0}          {1:8.2f}       {2:8.2f}".format(k + 1, pa, inclin))
+        else:
+            print("No rotations applied (yet)")
+
+    def _select_weight(self, weight=None):
+        if weight is None:
+            return weight
+        elif weight == "mass":
+            return self.mass
+        elif weight == "lum":
+            return self.flux
+        print("ERROR: please specify a weight function as 'mass' or 'lum'")
+        return None
+
+    # ------------------------------------------------------------------ the fused path
+    def _weights_on_device(self, weights):
+        if weights is None:
+            return None
+        dtype = self._soa[0].dtype
+        w = engine.to_device(weights, dtype, self._soa[0].device).reshape(-1)
+        if w.numel() != self.npart:
+            raise ValueError("weights have %d entries for %d particles" % (w.numel(), self.npart))
+        return w
+
+    def _max_of(self, key, tensor):
+        if key not in self._absmax:
+            self._absmax[key] = engine.absmax(tensor)
+        return self._absmax[key]
+
+    def _fixed_scales(self, acc, w, n_total=None, reduce_max=None):
+        if acc.code != _lib.ACC_FIXED:
+            return None
+        vel = self._base[1]
+        max_v = 2.0 * max(self._max_of(("v", id(vel), k), vel[k]) for k in range(3))  # |row . v| <= sqrt(3) max|v_k|
+        max_w = 1.0 if w is None else self._max_of(("w", w.data_ptr(), w.numel()), w)
+        if reduce_max is not None:            # sharded runs agree on global bounds
+            max_w, max_v = reduce_max(max_w, max_v)
+        return engine.fixed_scales(n_total or self.npart, max_w, max_v)
+
+    def _run_fused(self, grid, w, sums, acc, scales, mats=None, nchain=None, nviews=1, mask=None, mask_mode=0):
+        pos, vel = self._base
+        if mats is None:
+            mats = self._chain if self._chain else [np.eye(3, dtype=np.float32)]
+            nchain = len(mats)
+        maps, cube = engine.new_accumulators(grid, sums, acc, nviews)
+        soa = (pos[0], pos[1], pos[2], vel[0], vel[1], vel[2])
+        engine.project_bin(grid, soa, w, np.stack(mats), nchain, nviews, sums, acc, scales, maps, cube, mask, mask_mode)
+        return maps, cube
+
+    def _mesh(self, grid):
+        px, py, _ = grid.centres()
+        gx, gy = np.meshgrid(px, py)
+        if self.output == "torch":
+            return torch.from_numpy(gx).to(grid.device), torch.from_numpy(gy).to(grid.device)
+        return gx, gy
+
+    @staticmethod
+    def _mask_arg(kwargs, mode):
+        mask = kwargs.pop("mask", None)
+        if mask is None:
+            return None, _lib.MASK_NONE
+        return engine.to_device(mask, torch.uint8).reshape(-1), mode
+
+    def velocity_moments(self, data=None, weights=None, weight_name=None, limXY=default_limXY,
+                         nXY=default_npoint, **kwargs):
+        """Weighted mass, mean velocity and dispersion maps (pynmap/pynmap.py:319-340)."""
+        if self._soa is None:
+            print("WARNING: no positions - Aborting")
+            return SnapMap(name="EmptyMap")
+        if weight_name is not None:
+            weights = self._select_weight(weight_name)
+        if data is None:
+            print("WARNING: using z component of V as data")
+            n2 = engine.expand_nxy(nXY)
+            if n2 is None:
+                print("ERROR: dimension of n should be 1 or 2")
+                X = Y = M = V = S = 0
+            else:
+                acc = engine.AccMode(kwargs.pop("accumulate", "f64"))
+                mask, mode = self._mask_arg(kwargs, _lib.MASK_AND_NONFINITE)
+                grid = engine.get_grid(limXY, n2[0], n2[1])
+                w = self._weights_on_device(weights)
+                sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2
+                scales = self._fixed_scales(acc, w)
+                maps, _ = self._run_fused(grid, w, sums, acc, scales, mask=mask, mask_mode=mode)
+                M, V, S = (self._out(t) for t in engine.finalize_vmaps(grid, maps, None, sums, acc, scales))
+                X, Y = self._mesh(grid)
+        else:
+            pos = self._materialise()[0]
+            X, Y, M, V, S = points_2vmaps(pos[0], pos[1], data, weights=weights, limXY=limXY, nXY=nXY, **kwargs)
+            X, Y, M, V, S = (self._conv(a) for a in (X, Y, M, V, S))
+        mydict = {"X": X, "Y": Y, "V": V, "M": M, "S": S}
+        mydict["PAs"] = self.PAs
+        mydict["inclinations"] = self.inclinations
+        return SnapMap(name="Velocity moments", input_dic=mydict)
+
+    def _conv(self, a):
+        if isinstance(a, torch.Tensor):
+            return self._out(a)
+        return a
+
+    def create_map(self, data=None, weights=None, weight_name=None, limXY=default_limXY,
+                   nXY=default_npoint, **kwargs):
+        """Weighted mean map of an arbitrary per-particle quantity (pynmap/pynmap.py:421-437)."""
+        if weight_name is not None:
+            weights = self._select_weight(weight_name)
+        if data is None:
+            data = self.mass
+        pos = self._materialise()[0]
+        X, Y, W, D, DW = points_2map(pos[0], pos[1], data, weights=weights, limXY=limXY, nXY=nXY, **kwargs)
+        X, Y, W, D, DW = (self._conv(a) for a in (X, Y, W, D, DW))
+        mydict = {"X": X, "Y": Y, "W": W, "D": D, "DW": DW}
+        mydict["PAs"] = self.PAs
+        mydict["inclinations"] = self.inclinations
+        return SnapMap(name="map", input_dic=mydict)
+
+    def create_losvds(self, data=None, weights=None, weight_name=None, limXY=default_limXY,
+                      nXY=default_npoint, limV=default_limV, nV=default_nVpoint, **kwargs):
+        """Line-of-sight velocity distributions on a grid (pynmap/pynmap.py:439-455)."""
+        if weight_name is not None:
+            weights = self._select_weight(weight_name)
+        if data is None:
+            n2 = engine.expand_nxy(nXY)
+            if n2 is None:
+                print("ERROR: dimension of n should be 1 or 2")
+                return 0, 0, 0, 0, 0
+            acc = engine.AccMode(kwargs.pop("accumulate", "f64"))
+            mask, mode = self._mask_arg(kwargs, _lib.MASK_PLAIN)
+            w = self._weights_on_device(weights)
+            if mask is not None and w is not None and bool(mask.any()):
+                raise ValueError("The weights and list don't have the same length.")   # grid.py:251-259
+            grid = engine.get_grid(limXY, n2[0], n2[1], limV, int(nV))
+            scales = self._fixed_scales(acc, w)
+            _, cube = self._run_fused(grid, w, _lib.SUM_CUBE, acc, scales, mask=mask, mask_mode=mode)
+            px, py, pv = grid.centres()
+            mylosvd = LOSVD(px, py, pv, self._out(engine.finalize_cube(grid, cube, acc, scales)))
+        else:
+            pos = self._materialise()[0]
+            mylosvd = points_2losvds(pos[0], pos[1], data, weights=weights, limXY=limXY, nXY=nXY,
+                                     limV=limV, nV=nV, **kwargs)
+            if isinstance(mylosvd, LOSVD):
+                mylosvd.losvd = self._conv(mylosvd.losvd)
+        mylosvd.PAs = self.PAs
+        mylosvd.inclinations = self.inclinations
+        return mylosvd
+
+    # ------------------------------------------------------------------ additions (single read)
+    def project(self, weights=None, weight_name=None, limXY=default_limXY, nXY=default_npoint,
+                limV=default_limV, nV=default_nVpoint, accumulate="f64", reducer=None):
+        """velocity_moments + create_losvds from ONE pass over the particles: returns
+        (SnapMap, LOSVD) identical to calling the two methods separately.  The map's sum of
+        weights is recovered from the cube (plus an out-of-range remainder), which saves one
+        atomic per particle.  ``reducer(maps, cube)`` is the multi-GPU hook (sharded.py)."""
+        if weight_name is not None:
+            weights = self._select_weight(weight_name)
+        n2 = engine.expand_nxy(nXY)
+        acc = engine.AccMode(accumulate)
+        grid = engine.get_grid(limXY, n2[0], n2[1], limV, int(nV))
+        w = self._weights_on_device(weights)
+        sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2 | _lib.SUM_CUBE | _lib.W_FROM_CUBE
+        n_total, reduce_max = (reducer.n_total(self.npart), reducer.reduce_max) if reducer else (None, None)
+        scales = self._fixed_scales(acc, w, n_total, reduce_max)
+        maps, cube = self._run_fused(grid, w, sums, acc, scales)
+        if reducer is not None:
+            keep = reducer(maps, cube)
+            if not keep:
+                return None, None
+        M, V, S = (self._out(t) for t in engine.finalize_vmaps(grid, maps, cube, sums, acc, scales))
+        X, Y = self._mesh(grid)
+        newmap = SnapMap(name="Velocity moments", input_dic={"X": X, "Y": Y, "V": V, "M": M, "S": S,
+                                                              "PAs": self.PAs, "inclinations": self.inclinations})
+        px, py, pv = grid.centres()
+        mylosvd = LOSVD(px, py, pv, self._out(engine.finalize_cube(grid, cube, acc, scales)))
+        mylosvd.PAs, mylosvd.inclinations = self.PAs, self.inclinations
+        return newmap, mylosvd
+
+    def project_views(self, PAs, inclinations, weights=None, weight_name=None, limXY=default_limXY,
+                      nXY=default_npoint, accumulate="f64", direct=True):
+        """Moment maps for many viewing angles from ONE read of the particles (the reference
+        needs a Python loop of rotate() + velocity_moments(), pynmap.py:277-282).  Each view
+        starts from the original configuration, like rotate(reset=True).  Returns a list of SnapMap."""
+        if weight_name is not None:
+            weights = self._select_weight(weight_name)
+        n2 = engine.expand_nxy(nXY)
+        acc = engine.AccMode(accumulate)
+        grid = engine.get_grid(limXY, n2[0], n2[1])
+        w = self._weights_on_device(weights)
+        sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2
+        saved = (self._base, self._chain)
+        self._base, self._chain = self._soa, []
+        try:
+            scales = self._fixed_scales(acc, w)
+            out = []
+            pas = [np.float32(p) for p in PAs]
+            incs = [np.float32(i) for i in inclinations]
+            for s in range(0, len(pas), _lib.MAX_VIEWS):
+                mats = [rotation_matrix(p, i, direct=direct) for p, i in zip(pas[s:s + _lib.MAX_VIEWS], incs[s:s + _lib.MAX_VIEWS])]
+                maps, _ = self._run_fused(grid, w, sums, acc, scales, mats=mats, nchain=1, nviews=len(mats))
+                X, Y = self._mesh(grid)
+                for k in range(len(mats)):
+                    view = maps[k * grid.maps_elems:(k + 1) * grid.maps_elems]
+                    M, V, S = (self._out(t) for t in engine.finalize_vmaps(grid, view, None, sums, acc, scales))
+                    out.append(SnapMap(name="Velocity moments", input_dic={
+                        "X": X, "Y": Y, "V": V, "M": M, "S": S, "PAs": [pas[s + k]], "inclinations": [incs[s + k]]}))
+        finally:
+            self._base, self._chain = saved
+        return out
