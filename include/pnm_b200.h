@@ -164,11 +164,24 @@ int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv,
 int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream);
 
 /* ---- host-buffer path: what a reference user calls, end to end -------------------------------
- * Particle arrays live in HOST memory (pinned or pageable).  The call streams them through an
- * internal device staging ring in chunks, overlapping the copies with pnm_project_bin, then
- * finalises and copies the results back to HOST buffers (any may be NULL):
+ * Particle arrays live in HOST memory (pinned or pageable).  pnm_accumulate_host streams them
+ * through an internal device staging ring in chunks (H2D copy of chunk c+1 overlapping the
+ * pnm_project_bin kernel of chunk c) and adds into the caller's DEVICE accumulators; `stream`
+ * is made to wait for the binning, and the call returns once the host arrays have been consumed
+ * (they may be reused).  One view (nviews = 1).  device = CUDA ordinal.                        */
+int pnm_accumulate_host(const pnm_grid* g, int device, int64_t n, int dtype,
+                        const void* x_host, const void* y_host, const void* z_host,
+                        const void* vx_host, const void* vy_host, const void* vz_host,
+                        const void* w_host,
+                        const float* mats_host, int nchain,
+                        int sums, int acc_mode, const double* scales3_host,
+                        void* acc_maps, void* acc_cube, void* stream);
+
+/* pnm_project_host = grid + pnm_accumulate_host + finalise (+ smoothing of the cube when taps are
+ * given) + copy of the results to HOST buffers (any may be NULL):
  *   M, V, S : float64 (ny, nx);   cube : float64 (nx, ny, nv).
- * Synchronous: returns when the outputs are in host memory.  device = CUDA ordinal.          */
+ * i.e. snapshot.rotate -> velocity_moments -> create_losvds -> LOSVD.convolve_spatial
+ * (pynmap.py:246-285, :319-340, :439-455, losvd.py:94-141) in one synchronous call.            */
 int pnm_project_host(int device, int64_t n, int dtype,
                      const void* x_host, const void* y_host, const void* z_host,
                      const void* vx_host, const void* vy_host, const void* vz_host,
@@ -177,6 +190,7 @@ int pnm_project_host(int device, int64_t n, int dtype,
                      int32_t nx, const double* edges_x_host, int32_t ny, const double* edges_y_host,
                      int32_t nv, const double* edges_v_host,
                      int acc_mode, const double* scales3_host,
+                     const double* taps0_host, int32_t ntaps0, const double* taps1_host, int32_t ntaps1,
                      double* M_host, double* V_host, double* S_host, double* cube_host);
 /* frees the staging ring pnm_project_host keeps between calls */
 int pnm_host_release(void);

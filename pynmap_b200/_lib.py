@@ -41,9 +41,12 @@ _SIGNATURES = {
                                 POINTER(c_double), c_int32, _P]),
     "pnm_cube_moments": (c_int, [_P, c_int32, c_int32, c_int32, _P, c_double, _P, _P, _P, _P]),
     "pnm_absmax": (c_int, [_P, c_int64, c_int, _P, _P]),
+    "pnm_accumulate_host": (c_int, [_P, c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(c_float), c_int,
+                                    c_int, c_int, POINTER(c_double), _P, _P, _P]),
     "pnm_project_host": (c_int, [c_int, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, POINTER(c_float), c_int,
                                  c_int32, POINTER(c_double), c_int32, POINTER(c_double), c_int32,
-                                 POINTER(c_double), c_int, POINTER(c_double), _P, _P, _P, _P]),
+                                 POINTER(c_double), c_int, POINTER(c_double),
+                                 POINTER(c_double), c_int32, POINTER(c_double), c_int32, _P, _P, _P, _P]),
     "pnm_host_release": (c_int, []),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -1,10 +1,12 @@
-// pnm_host.cu -- pnm_project_host: the end-to-end entry point for callers whose particles live in
-// HOST memory (what a pynmap user has after snapshot.read, pynmap/pynmap.py:182-232).
+// pnm_host.cu -- entry points for callers whose particles live in HOST memory (what a pynmap user
+// has after snapshot.read, pynmap/pynmap.py:182-232).
 //
-// The arrays are cut into chunks; each chunk is copied H2D into one slot of a small staging ring
-// and binned by pnm_project_bin on the same stream, so that the PCIe copy of chunk c+1 overlaps
-// the kernel of chunk c (copy engine vs SMs).  All chunks add into one set of accumulators (the
-// scatter is atomic), then the maps / cube are finalised and copied back.
+//   pnm_accumulate_host  streams host arrays through a small device staging ring in chunks; the
+//                        H2D copy of chunk c+1 (copy engine) overlaps the pnm_project_bin kernel of
+//                        chunk c (SMs).  All chunks add into the caller's device accumulators.
+//   pnm_project_host     grid + accumulate + finalise (+ optional smoothing) + D2H of the results:
+//                        snapshot.rotate -> velocity_moments -> create_losvds -> convolve_spatial in
+//                        one call, host buffers in and out.
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -17,15 +19,15 @@
 namespace {
 
 constexpr int kSlots = 3;
-constexpr int64_t kChunk = 1 << 22;   // particles per chunk: 7 x 16 MiB (f32) per slot
+constexpr int64_t kChunk = 1 << 22;   // particles per chunk: 7 x 16 MiB (float32) per slot
 
 struct HostRing {
     int device = -1;
     size_t slot_bytes = 0;            // bytes per array per slot
     void* buf[kSlots][7] = {};
     cudaStream_t stream[kSlots] = {};
-    void* acc = nullptr;              // accumulators + outputs arena
-    size_t acc_bytes = 0;
+    void* arena = nullptr;            // pnm_project_host: accumulators + outputs + smoothing scratch
+    size_t arena_bytes = 0;
 };
 
 HostRing g_ring;
@@ -44,7 +46,7 @@ void release_locked() {
         for (int a = 0; a < 7; ++a) { cudaFree(g_ring.buf[s][a]); g_ring.buf[s][a] = nullptr; }
         if (g_ring.stream[s]) { cudaStreamDestroy(g_ring.stream[s]); g_ring.stream[s] = nullptr; }
     }
-    cudaFree(g_ring.acc);
+    cudaFree(g_ring.arena);
     g_ring = HostRing();
 }
 
@@ -58,8 +60,8 @@ void release_locked() {
         }                                                                                 \
     } while (0)
 
-int ensure_ring(int device, size_t slot_bytes, size_t acc_bytes) {
-    if (g_ring.device != device || g_ring.slot_bytes < slot_bytes || g_ring.acc_bytes < acc_bytes) {
+int ensure_ring(int device, size_t slot_bytes, size_t arena_bytes) {
+    if (g_ring.device != device || g_ring.slot_bytes < slot_bytes) {
         release_locked();
         HOST_CUDA(cudaSetDevice(device));
         g_ring.device = device;
@@ -68,10 +70,63 @@ int ensure_ring(int device, size_t slot_bytes, size_t acc_bytes) {
             for (int a = 0; a < 7; ++a) HOST_CUDA(cudaMalloc(&g_ring.buf[s][a], slot_bytes));
         }
         g_ring.slot_bytes = slot_bytes;
-        HOST_CUDA(cudaMalloc(&g_ring.acc, acc_bytes));
-        g_ring.acc_bytes = acc_bytes;
+    }
+    if (g_ring.arena_bytes < arena_bytes) {
+        cudaFree(g_ring.arena);
+        g_ring.arena = nullptr; g_ring.arena_bytes = 0;
+        HOST_CUDA(cudaMalloc(&g_ring.arena, arena_bytes));
+        g_ring.arena_bytes = arena_bytes;
     }
     return PNM_OK;
+}
+
+// Enqueue copy + bin of every chunk on the ring's streams; the caller's stream `after` (may be
+// null = legacy stream) is made to wait for all of them.  `before`: work the chunks must wait for.
+int accumulate_locked(const pnm_grid* grid, int device, int64_t n, int dtype, const void* const src[7],
+                      const float* mats_host, int nchain, int sums, int acc_mode, const double* scales3_host,
+                      void* acc_maps, void* acc_cube, cudaStream_t user) {
+    const size_t esz = dtype == PNM_F32 ? 4 : 8;
+    int rc = ensure_ring(device, (size_t)kChunk * 8, 0);
+    if (rc != PNM_OK) return rc;
+    cudaEvent_t ready = nullptr, done = nullptr;
+    HOST_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    HOST_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(ready, user);            // accumulators zeroed / earlier work on `user`
+    for (int s = 0; s < kSlots && e == cudaSuccess; ++s) e = cudaStreamWaitEvent(g_ring.stream[s], ready, 0);
+    const int narr = src[6] ? 7 : 6;
+    int64_t off = 0;
+    for (int c = 0; off < n && e == cudaSuccess && rc == PNM_OK; ++c, off += kChunk) {
+        const int slot = c % kSlots;
+        const int64_t m = std::min<int64_t>(kChunk, n - off);
+        cudaStream_t st = g_ring.stream[slot];
+        for (int a = 0; a < narr && e == cudaSuccess; ++a)
+            e = cudaMemcpyAsync(g_ring.buf[slot][a], static_cast<const char*>(src[a]) + (size_t)off * esz,
+                                (size_t)m * esz, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) break;
+        void** b = g_ring.buf[slot];
+        rc = pnm_project_bin(grid, m, dtype, b[0], b[1], b[2], b[3], b[4], b[5], src[6] ? b[6] : nullptr, nullptr,
+                             PNM_MASK_NONE, mats_host, nchain, 1, sums, acc_mode, scales3_host, acc_maps, acc_cube, st);
+    }
+    for (int s = 0; s < kSlots && e == cudaSuccess; ++s) {    // join the ring into the user's stream
+        e = cudaEventRecord(done, g_ring.stream[s]);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(user, done, 0);
+    }
+    // the host arrays may be reused by the caller as soon as we return: wait for the copies
+    for (int s = 0; s < kSlots; ++s) { cudaError_t t = cudaStreamSynchronize(g_ring.stream[s]); if (e == cudaSuccess) e = t; }
+    cudaEventDestroy(ready);
+    cudaEventDestroy(done);
+    if (rc != PNM_OK) return rc;                              // message set by pnm_project_bin
+    if (e != cudaSuccess) {
+        snprintf(g_host_err, sizeof(g_host_err), "pnm_accumulate_host: %s", cudaGetErrorString(e));
+        return host_fail(PNM_ECUDA);
+    }
+    return PNM_OK;
+}
+
+bool bad_arrays(int64_t n, int dtype, const void* const src[7], const float* mats) {
+    if (n < 0 || (dtype != PNM_F32 && dtype != PNM_F64) || !mats) return true;
+    for (int a = 0; a < 6; ++a) if (n > 0 && !src[a]) return true;
+    return false;
 }
 
 }  // namespace
@@ -84,21 +139,40 @@ int pnm_host_release(void) {
     return PNM_OK;
 }
 
+int pnm_accumulate_host(const pnm_grid* g, int device, int64_t n, int dtype,
+                        const void* x, const void* y, const void* z,
+                        const void* vx, const void* vy, const void* vz, const void* w,
+                        const float* mats_host, int nchain, int sums, int acc_mode, const double* scales3_host,
+                        void* acc_maps, void* acc_cube, void* stream) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    const void* src[7] = {x, y, z, vx, vy, vz, w};
+    if (!g || bad_arrays(n, dtype, src, mats_host)) {
+        snprintf(g_host_err, sizeof(g_host_err), "pnm_accumulate_host: bad argument");
+        return host_fail(PNM_EINVAL);
+    }
+    HOST_CUDA(cudaSetDevice(device));
+    return accumulate_locked(g, device, n, dtype, src, mats_host, nchain, sums, acc_mode, scales3_host, acc_maps,
+                             acc_cube, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int pnm_project_host(int device, int64_t n, int dtype,
                      const void* x, const void* y, const void* z,
                      const void* vx, const void* vy, const void* vz, const void* w,
                      const float* mats_host, int nchain,
                      int32_t nx, const double* ex, int32_t ny, const double* ey, int32_t nv, const double* ev,
                      int acc_mode, const double* scales3_host,
+                     const double* taps0_host, int32_t ntaps0, const double* taps1_host, int32_t ntaps1,
                      double* M_host, double* V_host, double* S_host, double* cube_host) {
     std::lock_guard<std::mutex> lock(g_mutex);
     g_host_err[0] = 0;
-    if (n < 0 || (dtype != PNM_F32 && dtype != PNM_F64) || !x || !y || !z || !vx || !vy || !vz || !mats_host) {
+    const void* src[7] = {x, y, z, vx, vy, vz, w};
+    if (bad_arrays(n, dtype, src, mats_host)) {
         snprintf(g_host_err, sizeof(g_host_err), "pnm_project_host: bad argument");
         return host_fail(PNM_EINVAL);
     }
     const bool want_maps = M_host || V_host || S_host;
     const bool want_cube = cube_host != nullptr;
+    const bool smooth = want_cube && ntaps0 > 0 && ntaps1 > 0 && taps0_host && taps1_host;
     if (!want_maps && !want_cube) {
         snprintf(g_host_err, sizeof(g_host_err), "pnm_project_host: no output requested");
         return host_fail(PNM_EINVAL);
@@ -108,8 +182,6 @@ int pnm_project_host(int device, int64_t n, int dtype,
         return host_fail(PNM_EINVAL);
     }
     HOST_CUDA(cudaSetDevice(device));
-    const size_t esz = dtype == PNM_F32 ? 4 : 8;
-    const int64_t chunk = std::min<int64_t>(kChunk, std::max<int64_t>(n, 1));
 
     pnm_grid* grid = nullptr;
     int rc = pnm_grid_create(nx, ex, ny, ey, want_cube ? nv : 0, want_cube ? ev : nullptr, &grid);
@@ -117,14 +189,16 @@ int pnm_project_host(int device, int64_t n, int dtype,
 
     const int64_t maps_elems = pnm_maps_acc_elems(grid), cube_elems = pnm_cube_acc_elems(grid);
     const int64_t npix = (int64_t)nx * ny;
-    // arena: [maps acc | cube acc | M V S]
-    const size_t acc_bytes = (size_t)(maps_elems + cube_elems + 3 * npix) * 8;
-    rc = ensure_ring(device, (size_t)kChunk * 8, acc_bytes);
+    // arena: [maps acc | cube acc | M V S | smoothing out | smoothing scratch]
+    const size_t arena_bytes = (size_t)(maps_elems + cube_elems + 3 * npix + (smooth ? 2 * cube_elems : 0)) * 8;
+    rc = ensure_ring(device, (size_t)kChunk * 8, arena_bytes);
     if (rc != PNM_OK) { pnm_grid_destroy(grid); return rc; }
-    char* arena = static_cast<char*>(g_ring.acc);
+    char* arena = static_cast<char*>(g_ring.arena);
     void* acc_maps = arena;
     void* acc_cube = arena + (size_t)maps_elems * 8;
     double* out_maps = reinterpret_cast<double*>(arena + (size_t)(maps_elems + cube_elems) * 8);
+    double* smooth_out = out_maps + 3 * npix;
+    double* smooth_work = smooth_out + cube_elems;
 
     int sums = 0;
     if (want_maps) sums |= PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2;
@@ -133,38 +207,12 @@ int pnm_project_host(int device, int64_t n, int dtype,
 
     cudaStream_t s0 = g_ring.stream[0];
     cudaError_t e = cudaMemsetAsync(arena, 0, (size_t)(maps_elems + cube_elems) * 8, s0);
-    cudaEvent_t zeroed = nullptr, done[kSlots] = {};
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&zeroed, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventRecord(zeroed, s0);
-    for (int s = 1; s < kSlots && e == cudaSuccess; ++s) e = cudaStreamWaitEvent(g_ring.stream[s], zeroed, 0);
-
-    const void* src[7] = {x, y, z, vx, vy, vz, w};
-    const int narr = w ? 7 : 6;
-    int64_t off = 0;
-    for (int c = 0; off < n && e == cudaSuccess && rc == PNM_OK; ++c, off += chunk) {
-        const int slot = c % kSlots;
-        const int64_t m = std::min(chunk, n - off);
-        cudaStream_t st = g_ring.stream[slot];
-        for (int a = 0; a < narr && e == cudaSuccess; ++a)
-            e = cudaMemcpyAsync(g_ring.buf[slot][a], static_cast<const char*>(src[a]) + (size_t)off * esz,
-                                (size_t)m * esz, cudaMemcpyHostToDevice, st);
-        if (e != cudaSuccess) break;
-        void** b = g_ring.buf[slot];
-        rc = pnm_project_bin(grid, m, dtype, b[0], b[1], b[2], b[3], b[4], b[5], w ? b[6] : nullptr, nullptr,
-                             PNM_MASK_NONE, mats_host, nchain, 1, sums, acc_mode, scales3_host,
-                             want_maps ? acc_maps : nullptr, want_cube ? acc_cube : nullptr, st);
-        if (rc != PNM_OK) snprintf(g_host_err, sizeof(g_host_err), "%s", pnm_last_error());
-    }
-    // join the slot streams into s0
-    for (int s = 1; s < kSlots && e == cudaSuccess && rc == PNM_OK; ++s) {
-        e = cudaEventCreateWithFlags(&done[s], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventRecord(done[s], g_ring.stream[s]);
-        if (e == cudaSuccess) e = cudaStreamWaitEvent(s0, done[s], 0);
-    }
+    if (e == cudaSuccess)
+        rc = accumulate_locked(grid, device, n, dtype, src, mats_host, nchain, sums, acc_mode, scales3_host,
+                               want_maps ? acc_maps : nullptr, want_cube ? acc_cube : nullptr, s0);
     if (e == cudaSuccess && rc == PNM_OK && want_maps) {
         rc = pnm_finalize_vmaps(grid, acc_maps, want_cube ? acc_cube : nullptr, sums, acc_mode, scales3_host,
                                 out_maps, out_maps + npix, out_maps + 2 * npix, nullptr, nullptr, s0);
-        if (rc != PNM_OK) snprintf(g_host_err, sizeof(g_host_err), "%s", pnm_last_error());
         double* hosts[3] = {M_host, V_host, S_host};
         for (int k = 0; k < 3 && e == cudaSuccess && rc == PNM_OK; ++k)
             if (hosts[k]) e = cudaMemcpyAsync(hosts[k], out_maps + k * npix, (size_t)npix * 8, cudaMemcpyDeviceToHost, s0);
@@ -172,20 +220,21 @@ int pnm_project_host(int device, int64_t n, int dtype,
     if (e == cudaSuccess && rc == PNM_OK && want_cube) {
         rc = pnm_finalize_cube(grid, acc_cube, acc_mode, acc_mode == PNM_ACC_FIXED ? scales3_host[0] : 1.0,
                                static_cast<double*>(acc_cube), s0);
-        if (rc != PNM_OK) snprintf(g_host_err, sizeof(g_host_err), "%s", pnm_last_error());
-        if (rc == PNM_OK) e = cudaMemcpyAsync(cube_host, acc_cube, (size_t)cube_elems * 8, cudaMemcpyDeviceToHost, s0);
+        const double* result = static_cast<const double*>(acc_cube);
+        if (rc == PNM_OK && smooth) {
+            rc = pnm_smooth_cube(result, smooth_out, smooth_work, nx, ny, nv, taps0_host, ntaps0, taps1_host, ntaps1, s0);
+            result = smooth_out;
+        }
+        if (rc == PNM_OK) e = cudaMemcpyAsync(cube_host, result, (size_t)cube_elems * 8, cudaMemcpyDeviceToHost, s0);
     }
-    cudaError_t e2 = cudaSuccess;
-    for (int s = 0; s < kSlots; ++s) { cudaError_t t = cudaStreamSynchronize(g_ring.stream[s]); if (e2 == cudaSuccess) e2 = t; }
-    if (zeroed) cudaEventDestroy(zeroed);
-    for (int s = 1; s < kSlots; ++s) if (done[s]) cudaEventDestroy(done[s]);
+    cudaError_t e2 = cudaStreamSynchronize(s0);
     pnm_grid_destroy(grid);
+    if (rc != PNM_OK) return rc;
     if (e == cudaSuccess) e = e2;
     if (e != cudaSuccess) {
         snprintf(g_host_err, sizeof(g_host_err), "pnm_project_host: %s", cudaGetErrorString(e));
         return host_fail(PNM_ECUDA);
     }
-    if (rc != PNM_OK) return host_fail(rc);
     return PNM_OK;
 }
 

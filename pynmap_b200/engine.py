@@ -209,11 +209,42 @@ def _scales_arg(acc, scales):
     return None
 
 
+class KernelTimer(object):
+    """Optional CUDA-event bracket around the scatter kernel (bench.py's roofline figure).
+    Events are recorded on the launching stream; read with ``total_ms`` after a synchronise."""
+
+    def __init__(self):
+        self.pairs = []
+
+    def bracket(self):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.pairs.append((a, b))
+        return a, b
+
+    def total_ms(self):
+        return sum(a.elapsed_time(b) for a, b in self.pairs)
+
+
+KERNEL_TIMER = None      # set to a KernelTimer to time every pnm_project_bin launch
+
+
 def project_bin(grid, soa, w, mats, nchain, nviews, sums, acc, scales, maps, cube, mask=None, mask_mode=0):
     """pnm_project_bin: soa = (x, y, z, vx, vy, vz) device tensors of one dtype."""
     x = soa[0]
     mats = np.ascontiguousarray(np.asarray(mats, dtype=np.float32).reshape(-1))
     assert mats.size == 9 * nchain * nviews
+    if KERNEL_TIMER is not None:
+        t0, t1 = KERNEL_TIMER.bracket()
+        t0.record()
+        try:
+            _project_bin_call(grid, x, soa, w, mats, nchain, nviews, sums, acc, scales, maps, cube, mask, mask_mode)
+        finally:
+            t1.record()
+        return
+    _project_bin_call(grid, x, soa, w, mats, nchain, nviews, sums, acc, scales, maps, cube, mask, mask_mode)
+
+
+def _project_bin_call(grid, x, soa, w, mats, nchain, nviews, sums, acc, scales, maps, cube, mask, mask_mode):
     _lib.call("pnm_project_bin", grid.handle, x.numel(), _TORCH_TO_PNM[x.dtype],
               ptr(soa[0]), ptr(soa[1]), ptr(soa[2]), ptr(soa[3]), ptr(soa[4]), ptr(soa[5]),
               ptr(w), ptr(mask), mask_mode,

@@ -119,8 +119,7 @@ class snapshot(object):
         """Build a snapshot from (N, 3) / (3, N)-SoA arrays or tensors instead of a file.
         ``output`` = 'torch' keeps results on the GPU, 'numpy' copies them to the host
         (default: 'torch' if ``pos`` is a CUDA tensor)."""
-        self = cls(snap_name=None, distance=distance, MLrecipe=MLrecipe, verbose=verbose,
-                   ml_function=ml_function) if False else cls.__new__(cls)
+        self = cls.__new__(cls)
         self.verbose = verbose
         self.distance = distance
         self.pc_per_arcsec = distance * np.pi / 0.648

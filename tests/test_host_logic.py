@@ -1,0 +1,61 @@
+"""CPU: host-side logic of the product (edges, matrices, scales, taps, shapes) against the golden
+vectors and the oracle -- no device needed."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as on
+from pynmap_b200 import engine, rotation
+from pynmap_b200.pynmap import convert_to_list
+
+
+def test_matrices_match_reference(golden):
+    g = golden("kat")
+    assert np.array_equal(rotation.rotation_matrix(30.0, 60.0), g["mat_f64ang"])
+    pa, inc = convert_to_list(30.0)[0], convert_to_list(60.0)[0]
+    assert isinstance(pa, np.float32)
+    assert np.array_equal(rotation.rotation_matrix(pa, inc), g["mat_f32ang"])
+    assert np.array_equal(rotation.rotation_matrix(30.0, 60.0, direct=False), g["mat_f64ang"].T)
+    assert np.array_equal(rotation.rotation_matrix_xyz(10., 20., 30., [2, 0, 1]), on.rotation_matrix_xyz(10., 20., 30., [2, 0, 1]))
+    with pytest.raises(ValueError):            # SURVEY 8c KAT 6: a list of angles does not work in the reference either
+        rotation.rotation_matrix(convert_to_list([30, 40])[0], convert_to_list([60, 70])[0])
+
+
+def test_edges_and_shapes():
+    for lo, hi, n in ((-15, 15, 256), (-1000, 1000, 100), (-1, 1, 3), (-12.5, 7.25, 511)):
+        e = engine.bin_edges(lo, hi, n)
+        half = (hi - lo) / (n - 1) / 2.
+        assert np.array_equal(e, np.linspace(lo - half, hi + half, n + 1))   # grid.py:119-124 verbatim
+        assert np.array_equal(e, on.bin_edges(lo, hi, n))
+    assert engine.expand_nxy(7) == (7, 7) and engine.expand_nxy((64, 32)) == (64, 32)
+    assert engine.expand_nxy(np.array([5])) == (5, 5) and engine.expand_nxy((1, 2, 3)) is None
+
+
+def test_fixed_scales_cannot_overflow():
+    for n, mw, md in ((10 ** 9, 3.0, 1200.0), (10 ** 6, 1e-3, 5.0), (1, 1.0, 1.0), (10 ** 8, 1e6, 1e4)):
+        s = engine.fixed_scales(n, mw, md)
+        for scale, bound in zip(s, (mw, mw * md, mw * md * md)):
+            assert math.frexp(scale)[0] == 0.5                 # a power of two
+            assert n * bound * scale <= 2.0 ** 62
+            assert n * bound * scale > 2.0 ** 60
+
+
+def test_gaussian_taps_match_astropy_statement():
+    for sx, sy in ((1.8, 1.8), (1.2, 2.7), (0.1, 0.1), (6.0, 2.0)):
+        s = engine.gaussian_support(sx, sy)
+        assert s % 2 == 1 and s == on.kernel_support(sx, sy)
+        t0, t1 = engine.gaussian_taps(sy, s), engine.gaussian_taps(sx, s)
+        k2 = on.gaussian_kernel2d(sx, sy)
+        assert np.allclose(np.outer(t0, t1), k2, rtol=1e-13, atol=1e-300)
+    assert engine.gaussian_support(0.1, 0.1) == 1
+    assert abs(engine.FWHM_TO_SIGMA - on.FWHM_TO_SIGMA) == 0
+
+
+def test_result_dtype_follows_numpy():
+    import torch
+    f32, f64, i64 = np.zeros(2, np.float32), np.zeros(2, np.float64), np.zeros(2, np.int64)
+    assert engine.result_dtype(f32) == torch.float32 and engine.result_dtype(f32, f32) == torch.float32
+    assert engine.result_dtype(f32, f64) == torch.float64 and engine.result_dtype(i64) == torch.float64
+    assert engine.result_dtype(torch.zeros(2), None) == torch.float32
+    assert engine.result_dtype(torch.zeros(2, dtype=torch.float64)) == torch.float64
