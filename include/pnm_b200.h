@@ -101,16 +101,23 @@ int pnm_grid_create(int32_t nx, const double* edges_x_host, int32_t ny, const do
                     int32_t nv, const double* edges_v_host, pnm_grid** out);
 int pnm_grid_destroy(pnm_grid* g);
 
-/* accumulator geometry for a grid: number of 8-byte elements in the maps and cube accumulators */
-int64_t pnm_maps_acc_elems(const pnm_grid* g); /* ny*nx*PNM_MAP_SLOTS */
-int64_t pnm_cube_acc_elems(const pnm_grid* g); /* nx*ny*nv            */
+/* Accumulators are OPAQUE 8-byte-element buffers owned by the caller (zero them before the first
+ * call; calls add).  Their internal layout is chosen for the L2 reduction units, not for the
+ * reader: the maps accumulator holds pnm_grid_map_replicas() copies of [iy][ix][4] that are summed
+ * at finalisation, the cube accumulator is velocity-major.  Sizes per view, in 8-byte elements:  */
+int64_t pnm_maps_acc_elems(const pnm_grid* g); /* replicas*ny*nx*PNM_MAP_SLOTS */
+int64_t pnm_cube_acc_elems(const pnm_grid* g); /* nx*ny*nv                     */
+int pnm_grid_map_replicas(const pnm_grid* g);
+/* Sums the map replicas into the first one (and clears the rest), so that a multi-GPU reduction
+ * only has to move the first ny*nx*PNM_MAP_SLOTS elements.                                      */
+int pnm_fold_maps(const pnm_grid* g, void* acc_maps, int acc_mode, void* stream);
 
 /* ---- fused rotate + project + bin (a1+a2+a3+a4) ---------------------------------------------
  * For each of `nviews` views: apply `nchain` float32 matrices in sequence to (x,y,z) and
  * (vx,vy,vz) (each step rounded like pnm_rotate), take x' = pos'[0], y' = pos'[1],
  * d = vel'[2], then accumulate the sums selected by `sums` with weights w (NULL = 1):
- *   acc_maps [view][iy][ix][4]   8-byte elements (double or int64 by acc_mode)
- *   acc_cube [view][ix][iy][iv]  8-byte elements
+ *   acc_maps [view][pnm_maps_acc_elems]   (double or int64 by acc_mode)
+ *   acc_cube [view][pnm_cube_acc_elems]
  * mats_host: float32 [nviews][nchain][9] on the HOST.  scales3_host (FIXED only): the three
  * power-of-two scales for w, w*d, w*d*d.  Accumulators must be zeroed by the caller (or hold
  * earlier partial sums: calls add).  mask: optional uint8 per particle.                       */
@@ -139,7 +146,7 @@ int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_
                        double* M, double* V, double* S, double* S1, double* S2, void* stream);
 int pnm_finalize_map(const pnm_grid* g, const void* acc_maps, int acc_mode,
                      const double* scales3_host, double* W, double* D, double* DW, void* stream);
-/* FIXED accumulators -> float64 cube, in place allowed (cube_out == acc_cube) */
+/* cube accumulator -> float64 cube[ix][iy][iv] (the layout of np.histogramdd, grid.py:259); not in place */
 int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int acc_mode, double scale_w,
                       double* cube_out, void* stream);
 

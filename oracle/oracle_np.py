@@ -172,7 +172,8 @@ def _weighted_hist(flat, keep, weights, size):
     """np.bincount: sequential float64 accumulation in particle order."""
     if weights is None:
         return np.bincount(flat[keep], minlength=size).astype(np.float64)
-    return np.bincount(flat[keep], weights=np.asarray(weights)[keep], minlength=size)
+    # histogramdd returns float64 even for empty input (bincount alone would give intp there)
+    return np.bincount(flat[keep], weights=np.asarray(weights)[keep], minlength=size).astype(np.float64)
 
 
 def hist2d(x, y, ex, ey, weights=None):

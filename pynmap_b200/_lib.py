@@ -30,6 +30,8 @@ _SIGNATURES = {
     "pnm_grid_destroy": (c_int, [_P]),
     "pnm_maps_acc_elems": (c_int64, [_P]),
     "pnm_cube_acc_elems": (c_int64, [_P]),
+    "pnm_grid_map_replicas": (c_int, [_P]),
+    "pnm_fold_maps": (c_int, [_P, _P, c_int, _P]),
     "pnm_project_bin": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int,
                                 POINTER(c_float), c_int, c_int, c_int, c_int, POINTER(c_double), _P, _P, _P]),
     "pnm_bin_points": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int,

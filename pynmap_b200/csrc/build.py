@@ -43,7 +43,8 @@ def build(force=False, verbose=False):
     if not force and not is_stale():
         return LIB
     srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.isfile(os.path.join(HERE, s))]
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + srcs
+    extra = os.environ.get("PNM_NVCC_EXTRA", "").split()
+    cmd = [find_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp"] + srcs
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stdout))

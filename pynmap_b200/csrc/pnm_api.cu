@@ -1,7 +1,9 @@
 // pnm_api.cu -- extern "C" surface of libpnm_b200.so (see include/pnm_b200.h for the contract).
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -28,6 +30,12 @@ int fail(int code, const char* fmt, ...) {
                         __FILE__, __LINE__);                                                 \
     } while (0)
 
+// development knobs (microbenchmarks only; defaults are the tuned values)
+inline int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 inline int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
@@ -46,6 +54,24 @@ template <> float thr_lower<float>(double e) {
     return f;
 }
 template <> double thr_lower<double>(double e) { return e; }
+// Guard band of the uniform bin guess g = (x - e0) * n / (en - e0), in units of bins: if the
+// fractional part of the COMPUTED g is further than this from 0 and 1, floor(g) is the true bin.
+// Two contributions: (1) how far the given edges deviate from the affine grid (np.linspace edges
+// are fl(fl(i*step)+start), a few ulps off), (2) the rounding of x0, inv, the subtraction and the
+// product in the particle dtype (unit roundoff u): |dg| <= 4u * (|x - x0| + |x0|) * inv.
+double guard_band(const double* e, int n, double u) {
+    if (n < 1 || !e) return 1.0;
+    const double inv = n / (e[n] - e[0]);
+    double dev = 0.0, amax = 0.0;
+    for (int i = 0; i <= n; ++i) {
+        dev = std::max(dev, std::fabs((e[i] - e[0]) * inv - i));
+        amax = std::max(amax, std::fabs(e[i]));
+    }
+    const double arith = 4.0 * u * ((e[n] - e[0]) + 2.0 * amax) * inv;
+    const double eps = 2.0 * (dev + arith) + 1e-9;       // x2 safety
+    return (eps < 0.25 && std::isfinite(eps)) ? eps : 1.0;   // 1.0: always decide on the table
+}
+
 template <typename T> T thr_last(double e);
 template <> float thr_last<float>(double e) {
     float f = (float)e;
@@ -59,10 +85,12 @@ template <> double thr_last<double>(double e) { return nextafter(e, INFINITY); }
 struct pnm_grid {
     int device;
     int nx, ny, nv;
+    int replicas;       // copies of the maps accumulator (power of two), see pnm_bin.cuh
     // per axis: thresholds in both particle dtypes, laid out [x | y | v]
     float* thr32;
     double* thr64;
     double x0, inv_dx, y0, inv_dy, v0, inv_dv;
+    double eps32[3], eps64[3];   // guard band (in bins) of the uniform guess for float32 / float64 data
 };
 
 extern "C" {
@@ -137,6 +165,17 @@ int pnm_grid_create(int32_t nx, const double* ex, int32_t ny, const double* ey,
     g->x0 = ex[0]; g->inv_dx = nx / (ex[nx] - ex[0]);
     g->y0 = ey[0]; g->inv_dy = ny / (ey[ny] - ey[0]);
     g->v0 = nv ? ev[0] : 0.0; g->inv_dv = nv ? nv / (ev[nv] - ev[0]) : 0.0;
+    for (int a = 0; a < 3; ++a) {
+        g->eps32[a] = guard_band(es[a], ns[a], 0x1p-24);
+        g->eps64[a] = guard_band(es[a], ns[a], 0x1p-53);
+    }
+    if ((int64_t)nx * ny * std::max(nv, 1) >= (1ll << 31))
+        { delete g; return fail(PNM_ELIMIT, "pnm_grid_create: more than 2^31 voxels"); }
+    // map replicas: as many as fit in 32 MiB of L2 (32 B per pixel), at most 64 (measured: 128^2 maps
+    // 9.2 ms with 1 replica, 2.3 ms with 32, 2.0 ms with 64 for 10^8 disk+bulge particles)
+    g->replicas = 1;
+    const int max_rep = env_int("PNM_MAX_REPLICAS", 64);
+    while (g->replicas < max_rep && (int64_t)nx * ny * PNM_MAP_SLOTS * 8 * (g->replicas * 2) <= ((int64_t)env_int("PNM_REPLICA_MIB", 32) << 20)) g->replicas *= 2;
     g->thr32 = nullptr; g->thr64 = nullptr;
     cudaError_t e = cudaGetDevice(&g->device);
     if (e == cudaSuccess) e = cudaMalloc(&g->thr32, total * sizeof(float));
@@ -159,7 +198,8 @@ int pnm_grid_destroy(pnm_grid* g) {
     return PNM_OK;
 }
 
-int64_t pnm_maps_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * PNM_MAP_SLOTS : 0; }
+int64_t pnm_maps_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * PNM_MAP_SLOTS * g->replicas : 0; }
+int pnm_grid_map_replicas(const pnm_grid* g) { return g ? g->replicas : 0; }
 int64_t pnm_cube_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * g->nv : 0; }
 
 }  // extern "C"
@@ -172,18 +212,32 @@ int launch_bin(const pnm::BinParams& p, int acc_mode, cudaStream_t st) {
     const size_t smem = (size_t)((p.nx + 1) + (p.ny + 1) + (p.nv + 1)) * sizeof(T);
     bool aligned = true;
     const void* ptrs[7] = {p.x, p.y, p.z, p.vx, p.vy, p.vz, p.w};
-    for (const void* q : ptrs) aligned = aligned && ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
-    const int64_t items = aligned ? (p.n + pnm::Vec<T>::N - 1) / pnm::Vec<T>::N : p.n;
-    const int grid = grid_for(items, 256, 8);
-#define PNM_LAUNCH(ACC, VL)                                                                          \
+    for (const void* q : ptrs) aligned = aligned && ((reinterpret_cast<uintptr_t>(q) & 31) == 0);   // 256-bit loads
+    const int64_t items = aligned ? (p.n + pnm::Pack<T>::N - 1) / pnm::Pack<T>::N : p.n;
+    const int grid = grid_for(items, 256, env_int("PNM_CTAS_PER_SM", PNM_MINBLOCKS));
+    // SIMPLE: one view, one matrix, no mask -> matrix in registers, cross-particle run merging
+    const bool simple = p.nviews == 1 && p.nchain == 1 && p.mask_mode == PNM_MASK_NONE;
+    // hot configurations get the set of sums as a compile-time constant (fused path only)
+    constexpr int kFull = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2 | PNM_SUM_CUBE | PNM_W_FROM_CUBE;
+    constexpr int kMaps = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2;
+#define PNM_LAUNCH(ACC, VL, SIMPLE, SUMS)                                                            \
     do {                                                                                             \
-        auto kern = pnm::k_project_bin<T, FUSED, ACC, VL>;                                           \
+        auto kern = pnm::k_project_bin<T, FUSED, ACC, VL, SIMPLE, SUMS>;                             \
         if (smem > 48 * 1024)                                                                        \
             PNM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, 256, smem, st>>>(p);                                                            \
     } while (0)
-    if (acc_mode == PNM_ACC_F64) { if (aligned) PNM_LAUNCH(PNM_ACC_F64, true); else PNM_LAUNCH(PNM_ACC_F64, false); }
-    else { if (aligned) PNM_LAUNCH(PNM_ACC_FIXED, true); else PNM_LAUNCH(PNM_ACC_FIXED, false); }
+#define PNM_LAUNCH2(ACC)                                                                             \
+    do {                                                                                             \
+        if (aligned && simple && FUSED && p.sums == kFull) PNM_LAUNCH(ACC, true, true, kFull);       \
+        else if (aligned && simple && FUSED && p.sums == kMaps) PNM_LAUNCH(ACC, true, true, kMaps);  \
+        else if (aligned && simple && FUSED && p.sums == PNM_SUM_CUBE) PNM_LAUNCH(ACC, true, true, PNM_SUM_CUBE); \
+        else if (aligned && simple) PNM_LAUNCH(ACC, true, true, -1);                                 \
+        else if (aligned) PNM_LAUNCH(ACC, true, false, -1);                                          \
+        else PNM_LAUNCH(ACC, false, false, -1);                                                      \
+    } while (0)
+    if (acc_mode == PNM_ACC_F64) PNM_LAUNCH2(PNM_ACC_F64); else PNM_LAUNCH2(PNM_ACC_FIXED);
+#undef PNM_LAUNCH2
 #undef PNM_LAUNCH
     PNM_CUDA(cudaGetLastError());
     return PNM_OK;
@@ -224,7 +278,11 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     if (dtype == PNM_F32) { p.thr_x = g->thr32 + ox; p.thr_y = g->thr32 + oy; p.thr_v = g->thr32 + ov; }
     else { p.thr_x = g->thr64 + ox; p.thr_y = g->thr64 + oy; p.thr_v = g->thr64 + ov; }
     p.x0 = g->x0; p.inv_dx = g->inv_dx; p.y0 = g->y0; p.inv_dy = g->inv_dy; p.v0 = g->v0; p.inv_dv = g->inv_dv;
+    const double* eps = dtype == PNM_F32 ? g->eps32 : g->eps64;
+    p.eps_x = eps[0]; p.eps_y = eps[1]; p.eps_v = eps[2];
     p.sums = sums; p.nchain = fused ? nchain : 1; p.nviews = fused ? nviews : 1;
+    p.replicas = g->replicas;
+    p.rep_shift = env_int("PNM_REP_SHIFT", 5);
     for (int k = 0; k < 3; ++k) p.scale[k] = (acc_mode == PNM_ACC_FIXED) ? scales3_host[k] : 1.0;
     p.acc_maps = acc_maps; p.acc_cube = acc_cube;
     p.maps_stride = pnm_maps_acc_elems(g); p.cube_stride = pnm_cube_acc_elems(g);
@@ -265,11 +323,11 @@ int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_
     const int grid = (npix + 255) / 256;
     if (acc_mode == PNM_ACC_F64) {
         pnm::k_finalize_vmaps<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, acc_cube, g->nx, g->ny, g->nv,
-                                                                              wfc, 1.0, 1.0, 1.0, M, V, S, S1, S2);
+                                                                              g->replicas, wfc, 1.0, 1.0, 1.0, M, V, S, S1, S2);
     } else if (acc_mode == PNM_ACC_FIXED) {
         if (!scales3_host) return fail(PNM_EINVAL, "pnm_finalize_vmaps: FIXED mode needs scales");
         pnm::k_finalize_vmaps<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(
-            acc_maps, acc_cube, g->nx, g->ny, g->nv, wfc, 1.0 / scales3_host[0], 1.0 / scales3_host[1],
+            acc_maps, acc_cube, g->nx, g->ny, g->nv, g->replicas, wfc, 1.0 / scales3_host[0], 1.0 / scales3_host[1],
             1.0 / scales3_host[2], M, V, S, S1, S2);
     } else {
         return fail(PNM_EINVAL, "pnm_finalize_vmaps: acc_mode %d", acc_mode);
@@ -284,10 +342,10 @@ int pnm_finalize_map(const pnm_grid* g, const void* acc_maps, int acc_mode, cons
     const int npix = g->nx * g->ny;
     const int grid = (npix + 255) / 256;
     if (acc_mode == PNM_ACC_F64) {
-        pnm::k_finalize_map<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, npix, 1.0, 1.0, W, D, DW);
+        pnm::k_finalize_map<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, npix, g->replicas, 1.0, 1.0, W, D, DW);
     } else if (acc_mode == PNM_ACC_FIXED) {
         if (!scales3_host) return fail(PNM_EINVAL, "pnm_finalize_map: FIXED mode needs scales");
-        pnm::k_finalize_map<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, npix, 1.0 / scales3_host[0],
+        pnm::k_finalize_map<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, npix, g->replicas, 1.0 / scales3_host[0],
                                                                               1.0 / scales3_host[1], W, D, DW);
     } else {
         return fail(PNM_EINVAL, "pnm_finalize_map: acc_mode %d", acc_mode);
@@ -299,15 +357,27 @@ int pnm_finalize_map(const pnm_grid* g, const void* acc_maps, int acc_mode, cons
 int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int acc_mode, double scale_w, double* cube_out,
                       void* stream) {
     if (!g || !acc_cube || !cube_out) return fail(PNM_EINVAL, "pnm_finalize_cube: null argument");
-    const int64_t n = pnm_cube_acc_elems(g);
-    if (acc_mode == PNM_ACC_F64) {
-        if (cube_out != acc_cube)
-            PNM_CUDA(cudaMemcpyAsync(cube_out, acc_cube, n * sizeof(double), cudaMemcpyDeviceToDevice, as_stream(stream)));
-        return PNM_OK;
-    }
-    if (acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_finalize_cube: acc_mode %d", acc_mode);
-    pnm::k_fixed_to_f64<<<grid_for(n, 256, 16), 256, 0, as_stream(stream)>>>((const long long*)acc_cube, cube_out, n,
-                                                                           1.0 / scale_w);
+    if (static_cast<const void*>(cube_out) == acc_cube) return fail(PNM_EINVAL, "pnm_finalize_cube: cannot run in place");
+    if (g->nv < 1) return fail(PNM_EINVAL, "pnm_finalize_cube: grid has no V axis");
+    const int npix = g->nx * g->ny;
+    const dim3 grid((npix + 31) / 32, (g->nv + 31) / 32), block(32, 8);
+    if (acc_mode == PNM_ACC_F64)
+        pnm::k_cube_out<PNM_ACC_F64><<<grid, block, 0, as_stream(stream)>>>(acc_cube, cube_out, npix, g->nv, 1.0);
+    else if (acc_mode == PNM_ACC_FIXED)
+        pnm::k_cube_out<PNM_ACC_FIXED><<<grid, block, 0, as_stream(stream)>>>(acc_cube, cube_out, npix, g->nv, 1.0 / scale_w);
+    else
+        return fail(PNM_EINVAL, "pnm_finalize_cube: acc_mode %d", acc_mode);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_fold_maps(const pnm_grid* g, void* acc_maps, int acc_mode, void* stream) {
+    if (!g || !acc_maps) return fail(PNM_EINVAL, "pnm_fold_maps: null argument");
+    const int64_t per = (int64_t)g->nx * g->ny * PNM_MAP_SLOTS;
+    const int grid = (int)((per + 255) / 256);
+    if (acc_mode == PNM_ACC_F64) pnm::k_fold_maps<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, per, g->replicas);
+    else if (acc_mode == PNM_ACC_FIXED) pnm::k_fold_maps<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, per, g->replicas);
+    else return fail(PNM_EINVAL, "pnm_fold_maps: acc_mode %d", acc_mode);
     PNM_CUDA(cudaGetLastError());
     return PNM_OK;
 }

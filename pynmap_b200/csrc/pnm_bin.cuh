@@ -1,14 +1,28 @@
 // pnm_bin.cuh -- fused rotate + project + bin kernel (K1+K2+K3 of SURVEY.md 2.2).
 //
-// One pass over the SoA particle arrays produces, per viewing angle,
-//   maps accumulator  [iy][ix][4] = { sum w (or the out-of-V-range remainder), sum w*d, sum w*d*d, - }
-//   cube accumulator  [ix][iy][iv] =   sum w
-// Reference semantics: rotation.py:115-117 (rotation), grid.py:121-131 / :200-201 (2-D moment
-// histograms, result transposed to [iy][ix]), grid.py:252-259 (3-D histogram, [ix][iy][iv]).
+// One pass over the SoA particle arrays produces, per viewing angle, the (opaque) accumulators
+//   maps  [view][replica][iy][ix][4] = { sum w (or its out-of-V-range remainder), sum w*d, sum w*d*d, - }
+//   cube  [view][iv][ix][iy]         =   sum w
+// which pnm_finalize_* turn into the reference's layouts.  Reference semantics:
+// rotation.py:115-117 (rotation), grid.py:121-131 / :200-201 (2-D moment histograms),
+// grid.py:252-259 (3-D histogram).
 //
-// Roofline: HBM.  Algorithmic bytes = 7 arrays x sizeof(T) per particle (28 B for float32);
-// the accumulators (<= 34 MB for the 128x128x256 cube) stay resident in the 126 MB L2, so the
-// scatter is served by L2 reduction units (REDG) and never touches HBM until eviction.
+// Roofline: HBM (28 B per float32 particle).  What actually bounds the kernel is the SM's
+// reduction-issue rate (~1.3 clk per scattered RED lane, measured), so the design minimises REDs
+// per particle, keeps the instruction stream short and spreads same-address traffic:
+//   * accumulators (<= 34 MB for 128x128x256) stay resident in the 126 MB L2; the particle stream
+//     is loaded with 256-bit LDG, no L1 allocation and an L2 evict-first policy;
+//   * maps are replicated R times (one replica per warp id) so that the galaxy-centre pixels, which
+//     receive ~2 % of all particles, do not serialise on one L2 sector;
+//   * the cube is stored velocity-major, which spreads the hot central spaxel over ~nv L2 lines
+//     instead of one 2 KB column;
+//   * consecutive particles of a thread that fall in the same pixel are merged in registers before
+//     the RED (free for random order, ~1 RED per run for space-filling-curve ordered snapshots);
+//   * with PNM_W_FROM_CUBE the map's sum w costs no RED at all for particles inside the V range;
+//   * bin lookup: the uniform guess floor((x-x0)*inv) is PROVABLY the numpy bin whenever its
+//     fractional part is further than `eps` from an integer (eps bounds the float rounding of the
+//     guess plus the deviation of np.linspace edges from an affine grid, computed at grid
+//     creation); only the ~2*eps fraction of near-edge particles consults the edge table.
 #pragma once
 #include "pnm_common.cuh"
 
@@ -24,98 +38,194 @@ struct BinParams {
     int nx, ny, nv;
     const void* thr_x; const void* thr_y; const void* thr_v;  // device tables, dtype of particles
     double x0, inv_dx, y0, inv_dy, v0, inv_dv;        // uniform-guess hints
+    double eps_x, eps_y, eps_v;                       // guard band of the guess, in bins (>= 0.5: table only)
     int sums;
     int nchain, nviews;
+    int replicas;                                     // power of two
+    int rep_shift;                                    // replica = (thread id >> rep_shift) & (replicas-1)
     double scale[3];
     void* acc_maps; void* acc_cube;
-    int64_t maps_stride, cube_stride;                 // 8-byte elements per view
+    int64_t maps_stride, cube_stride;                 // 8-byte elements per view (maps: all replicas)
     float mats[kMaxMats * 9];                         // [view][chain][9]
 };
 
-template <typename T> struct Vec;
-template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
-template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
-
-template <typename T>
-__device__ __forceinline__ void unpack(const float4& v, T* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-template <typename T>
-__device__ __forceinline__ void unpack(const double2& v, T* o) { o[0] = v.x; o[1] = v.y; }
-
-// streaming loads: read once -> no L1 allocation, L2 evict-first policy, so the stream does not
-// push the L2-resident accumulators out (a bare .L2::evict_first needs 256-bit loads; the
-// createpolicy / cache_hint form works at any width)
-__device__ __forceinline__ uint64_t make_stream_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ float4 ld_stream(const float4* p, uint64_t pol) {
-    float4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ double2 ld_stream(const double2* p, uint64_t pol) {
-    double2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0,%1}, [%2], %3;"
-                 : "=d"(r.x), "=d"(r.y) : "l"(p), "l"(pol));
-    return r;
-}
-
-// --------------------------------------------------------------------------------------------
-// One particle, all views.
-// --------------------------------------------------------------------------------------------
-template <typename T, bool FUSED, int ACC>
-__device__ __forceinline__ void bin_particle(const BinParams& p, const T* sx, const T* sy, const T* sv,
-                                             T x, T y, T z, T vx, T vy, T vz, T w, bool masked_in) {
-    const T x0 = (T)p.x0, idx = (T)p.inv_dx, y0 = (T)p.y0, idy = (T)p.inv_dy, v0 = (T)p.v0, idv = (T)p.inv_dv;
-    for (int view = 0; view < p.nviews; ++view) {
-        T px = x, py = y, d = vx;
-        if (FUSED) {
-            const float* m = p.mats + (size_t)view * p.nchain * 9;
-            T pz = z, qx = vx, qy = vy, qz = vz;
-            for (int c = 0; c < p.nchain - 1; ++c, m += 9) {   // compounded rotations keep all rows
-                T ax = rot_row(m[0], m[1], m[2], px, py, pz);
-                T ay = rot_row(m[3], m[4], m[5], px, py, pz);
-                T az = rot_row(m[6], m[7], m[8], px, py, pz);
-                T bx = rot_row(m[0], m[1], m[2], qx, qy, qz);
-                T by = rot_row(m[3], m[4], m[5], qx, qy, qz);
-                T bz = rot_row(m[6], m[7], m[8], qx, qy, qz);
-                px = ax; py = ay; pz = az; qx = bx; qy = by; qz = bz;
-            }
-            T ax = rot_row(m[0], m[1], m[2], px, py, pz);       // last step: sky x, sky y, v_los
-            T ay = rot_row(m[3], m[4], m[5], px, py, pz);
-            d = rot_row(m[6], m[7], m[8], qx, qy, qz);
-            px = ax; py = ay;
-        }
-        bool masked = masked_in;
-        if (p.mask_mode == PNM_MASK_AND_NONFINITE) masked = masked_in && !is_finite(d);
-        if (masked) continue;
-        const int ix = find_bin<T>(px, sx, p.nx, x0, idx);
-        const int iy = find_bin<T>(py, sy, p.ny, y0, idy);
-        if ((ix | iy) < 0) continue;
-        int iv = -1;
-        if (p.sums & PNM_SUM_CUBE) iv = find_bin<T>(d, sv, p.nv, v0, idv);
-
-        const int64_t pix = ((int64_t)iy * p.nx + ix) * PNM_MAP_SLOTS + view * p.maps_stride;
-        if (p.sums & PNM_SUM_W) {
-            if (!((p.sums & PNM_W_FROM_CUBE) && iv >= 0)) acc_add<ACC>(p.acc_maps, pix + 0, (double)w, p.scale[0]);
-        }
-        if (p.sums & PNM_SUM_WD) acc_add<ACC>(p.acc_maps, pix + 1, (double)mul_rn(w, d), p.scale[1]);
-        if (p.sums & PNM_SUM_WD2) acc_add<ACC>(p.acc_maps, pix + 2, (double)mul_rn(w, mul_rn(d, d)), p.scale[2]);
-        if (iv >= 0) {
-            const int64_t vox = ((int64_t)ix * p.ny + iy) * p.nv + iv + view * p.cube_stride;
-            acc_add<ACC>(p.acc_cube, vox, (double)w, p.scale[0]);
-        }
+// ---- 256-bit streaming loads (sm_100: LDG.E.256): read once -> no L1 allocation, L2 evict-first,
+// so the 2.8 GB stream does not push the L2-resident accumulators out.
+template <typename T> struct Pack;
+template <> struct Pack<float> {
+    static constexpr int N = 8;
+    __device__ __forceinline__ static void load(const float* p, float* o) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7])
+                     : "l"(p));
     }
+};
+template <> struct Pack<double> {
+    static constexpr int N = 4;
+    __device__ __forceinline__ static void load(const double* p, double* o) {
+        asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+    }
+};
+
+// ---- bin lookup --------------------------------------------------------------------------------
+template <typename T> struct Axis { T x0, inv, eps, one_m_eps, n_plus_half; int n; const T* thr; };
+
+// exact path: binary search in the table of thresholds (thr[i] <= x < thr[i+1], see pnm_grid_create),
+// independent of the guess, so it is exact for any monotone edges.  Out of line: it is rare.
+template <typename T>
+__device__ __noinline__ int exact_bin(T x, const T* thr, int n) {
+    if (!(x >= thr[0]) || !(x < thr[n])) return -1;     // below, above (closed last edge folded into thr[n]), NaN
+    int lo = 0, hi = n;                                  // invariant: thr[lo] <= x < thr[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (x >= thr[mid]) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
-// --------------------------------------------------------------------------------------------
-// Kernel: persistent grid-stride loop, 16-byte vector loads (4 float32 / 2 float64 particles per
-// thread per array), scalar tail.  VECLOAD=false is the path for unaligned array pointers.
-// --------------------------------------------------------------------------------------------
-template <typename T, bool FUSED, int ACC, bool VECLOAD>
-__global__ void __launch_bounds__(256) k_project_bin(const __grid_constant__ BinParams p) {
+__device__ __forceinline__ float floor_t(float v) { return floorf(v); }
+__device__ __forceinline__ double floor_t(double v) { return floor(v); }
+
+// uniform guess.  Inside the grid (give or take half a bin) `sure` is cleared when x is within eps
+// (in bins) of an edge; further out the particle is certainly dropped (-1), and so is NaN.
+template <typename T>
+__device__ __forceinline__ int guess_bin(T x, const Axis<T>& a, bool& sure) {
+    const T g = (x - a.x0) * a.inv;
+    const T f = floor_t(g);
+    const T r = g - f;
+    const bool inside = (g >= (T)-0.5) && (g <= a.n_plus_half);      // false for NaN
+    sure = sure && (!inside || ((r > a.eps) && (r < a.one_m_eps)));
+    return inside ? (int)f : -1;                                      // range checked by the caller
+}
+
+// ---- accumulator arithmetic --------------------------------------------------------------------
+template <int ACC> struct AccT { using type = double; };
+template <> struct AccT<PNM_ACC_FIXED> { using type = long long; };
+
+// FIXED: rint(value * 2^k); the product with a power of two is exact in the particle dtype, so
+// the float32 path needs no widening.  Non-finite values quantise to 0 (documented deviation: the
+// float64 path propagates NaN like the reference does).
+template <int ACC>
+__device__ __forceinline__ typename AccT<ACC>::type to_acc(float v, double scale) {
+    if (ACC == PNM_ACC_F64) return (typename AccT<ACC>::type)v;
+    const float s = v * (float)scale;
+    return (typename AccT<ACC>::type)(is_finite(s) ? __float2ll_rn(s) : 0ll);
+}
+template <int ACC>
+__device__ __forceinline__ typename AccT<ACC>::type to_acc(double v, double scale) {
+    if (ACC == PNM_ACC_F64) return (typename AccT<ACC>::type)v;
+    const double s = v * scale;
+    return (typename AccT<ACC>::type)(is_finite(s) ? __double2ll_rn(s) : 0ll);
+}
+
+// result unused -> REDG (RED.E.ADD.F64.RN / RED.E.ADD.64), no return trip
+__device__ __forceinline__ void red_add(double* p, double v) { atomicAdd(p, v); }
+__device__ __forceinline__ void red_add(long long* p, long long v) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
+}
+
+// pending run of map contributions that share one pixel (merged in registers)
+template <int ACC>
+struct MapRun {
+    using A = typename AccT<ACC>::type;
+    int off = -1;
+    A s0 = 0, s1 = 0, s2 = 0;
+    bool has0 = false;
+
+    __device__ __forceinline__ void flush(A* maps, int sums) {
+        if (off < 0) return;
+        if ((sums & PNM_SUM_W) && has0) red_add(maps + off, s0);
+        if (sums & PNM_SUM_WD) red_add(maps + off + 1, s1);
+        if (sums & PNM_SUM_WD2) red_add(maps + off + 2, s2);
+        off = -1;
+    }
+    __device__ __forceinline__ void add(A* maps, int sums, int o, bool use0, A a0, A a1, A a2) {
+        if (o != off) {
+            flush(maps, sums);
+            off = o; s0 = 0; s1 = a1; s2 = a2; has0 = false;
+        } else {
+            s1 += a1; s2 += a2;
+        }
+        if (use0) { s0 += a0; has0 = true; }
+    }
+};
+
+// ---- per-thread binning context: everything loop invariant sits in registers -------------------
+// SUMS >= 0: the set of sums is a compile-time constant (hot configurations); -1: read at run time.
+template <typename T, int ACC, int SUMS>
+struct Binner {
+    using A = typename AccT<ACC>::type;
+    Axis<T> ax, ay, av;
+    int rsums, nx, ny, npix, mask_mode;
+    double sc0, sc1, sc2;
+
+    __device__ __forceinline__ Binner(const BinParams& p, const T* sx, const T* sy, const T* sv) {
+        ax = {(T)p.x0, (T)p.inv_dx, (T)p.eps_x, (T)1 - (T)p.eps_x, (T)p.nx + (T)0.5, p.nx, sx};
+        ay = {(T)p.y0, (T)p.inv_dy, (T)p.eps_y, (T)1 - (T)p.eps_y, (T)p.ny + (T)0.5, p.ny, sy};
+        av = {(T)p.v0, (T)p.inv_dv, (T)p.eps_v, (T)1 - (T)p.eps_v, (T)p.nv + (T)0.5, p.nv, sv};
+        rsums = p.sums; nx = p.nx; ny = p.ny; npix = p.nx * p.ny; mask_mode = p.mask_mode;
+        sc0 = p.scale[0]; sc1 = p.scale[1]; sc2 = p.scale[2];
+    }
+    __device__ __forceinline__ int sums() const { return SUMS >= 0 ? SUMS : rsums; }
+
+    // (px, py, d) already projected
+    __device__ __forceinline__ void scatter(A* maps, A* cube, MapRun<ACC>& run, T px, T py, T d, T w, bool masked_in) {
+        if (masked_in) {
+            if (mask_mode == PNM_MASK_PLAIN) return;
+            if (mask_mode == PNM_MASK_AND_NONFINITE && !is_finite(d)) return;
+        }
+        const int sm = sums();
+        const bool want_v = (sm & PNM_SUM_CUBE) != 0;
+        bool sure = true;
+        int ix = guess_bin<T>(px, ax, sure);
+        int iy = guess_bin<T>(py, ay, sure);
+        int iv = want_v ? guess_bin<T>(d, av, sure) : -1;
+        if (!sure) {                                     // ~1e-3 of the particles
+            ix = exact_bin<T>(px, ax.thr, ax.n);
+            iy = exact_bin<T>(py, ay.thr, ay.n);
+            if (want_v) iv = exact_bin<T>(d, av.thr, av.n);
+        }
+        if ((unsigned)ix >= (unsigned)nx || (unsigned)iy >= (unsigned)ny) return;
+        const bool in_v = want_v && (unsigned)iv < (unsigned)av.n;
+        if (sm & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2)) {
+            const bool use0 = (sm & PNM_SUM_W) && !((sm & PNM_W_FROM_CUBE) && in_v);
+            run.add(maps, sm, (iy * nx + ix) * PNM_MAP_SLOTS, use0, to_acc<ACC>(w, sc0), to_acc<ACC>(mul_rn(w, d), sc1),
+                    to_acc<ACC>(mul_rn(w, mul_rn(d, d)), sc2));
+        }
+        if (in_v) red_add(cube + (iv * npix + ix * ny + iy), to_acc<ACC>(w, sc0));
+    }
+};
+
+// rotation chain of one view (general case: matrices read from the parameter bank)
+template <typename T>
+__device__ __forceinline__ void project_chain(const float* m, int nchain, T x, T y, T z, T vx, T vy, T vz,
+                                              T& px, T& py, T& d) {
+    T pz = z, qx = vx, qy = vy, qz = vz;
+    px = x; py = y;
+    for (int c = 0; c < nchain - 1; ++c, m += 9) {   // compounded rotations keep all rows
+        const T ax = rot_row(m[0], m[1], m[2], px, py, pz), ay = rot_row(m[3], m[4], m[5], px, py, pz),
+                az = rot_row(m[6], m[7], m[8], px, py, pz);
+        const T bx = rot_row(m[0], m[1], m[2], qx, qy, qz), by = rot_row(m[3], m[4], m[5], qx, qy, qz),
+                bz = rot_row(m[6], m[7], m[8], qx, qy, qz);
+        px = ax; py = ay; pz = az; qx = bx; qy = by; qz = bz;
+    }
+    const T ax = rot_row(m[0], m[1], m[2], px, py, pz);   // last step: only sky x, sky y and v_los are needed
+    const T ay = rot_row(m[3], m[4], m[5], px, py, pz);
+    d = rot_row(m[6], m[7], m[8], qx, qy, qz);
+    px = ax; py = ay;
+}
+
+// ---- kernel: persistent grid-stride loop; each thread takes Pack<T>::N consecutive particles per
+// array with one 256-bit load (VECLOAD), scalar path for the tail and for unaligned pointers.
+// SIMPLE = one view, one matrix, no mask: the matrix lives in registers and consecutive particles
+// of a thread merge their map contributions. ---------------------------------------------------
+#ifndef PNM_MINBLOCKS
+#define PNM_MINBLOCKS 2
+#endif
+template <typename T, bool FUSED, int ACC, bool VECLOAD, bool SIMPLE, int SUMS>
+__global__ void __launch_bounds__(256, PNM_MINBLOCKS) k_project_bin(const __grid_constant__ BinParams p) {
+    using A = typename AccT<ACC>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sx = reinterpret_cast<T*>(smem_raw);
     T* sy = sx + (p.nx + 1);
@@ -126,43 +236,71 @@ __global__ void __launch_bounds__(256) k_project_bin(const __grid_constant__ Bin
         for (int i = threadIdx.x; i <= p.nv; i += blockDim.x) sv[i] = static_cast<const T*>(p.thr_v)[i];
     __syncthreads();
 
-    using V = typename Vec<T>::type;
-    constexpr int VN = Vec<T>::N;
+    constexpr int VN = Pack<T>::N;
     const T* X = static_cast<const T*>(p.x);  const T* Y = static_cast<const T*>(p.y);
     const T* Z = static_cast<const T*>(p.z);  const T* VX = static_cast<const T*>(p.vx);
     const T* VY = static_cast<const T*>(p.vy); const T* VZ = static_cast<const T*>(p.vz);
     const T* W = static_cast<const T*>(p.w);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    // replica by warp id: lanes of a warp stay together, neighbouring warps spread out
+    const int rep = (int)((tid >> p.rep_shift) & (p.replicas - 1));
+    A* const maps0 = reinterpret_cast<A*>(p.acc_maps) + (int64_t)rep * p.nx * p.ny * PNM_MAP_SLOTS;
+    A* const cube0 = reinterpret_cast<A*>(p.acc_cube);
+    Binner<T, ACC, SUMS> B(p, sx, sy, sv);
+    float m[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) m[k] = p.mats[k];
+
+    auto one = [&](int64_t idx, T x, T y, T z, T vx, T vy, T vz, T w, MapRun<ACC>& run) {
+        if (SIMPLE) {
+            T px = x, py = y, d = vx;
+            if (FUSED) {
+                px = rot_row(m[0], m[1], m[2], x, y, z);
+                py = rot_row(m[3], m[4], m[5], x, y, z);
+                d = rot_row(m[6], m[7], m[8], vx, vy, vz);
+            }
+            B.scatter(maps0, cube0, run, px, py, d, w, false);
+        } else {
+            const bool masked = p.mask_mode != PNM_MASK_NONE && p.mask[idx] != 0;
+            for (int view = 0; view < p.nviews; ++view) {
+                T px = x, py = y, d = vx;
+                if (FUSED) project_chain<T>(p.mats + (size_t)view * p.nchain * 9, p.nchain, x, y, z, vx, vy, vz, px, py, d);
+                MapRun<ACC> vr;       // no cross-particle merging in the general path
+                A* maps = maps0 + view * p.maps_stride;
+                B.scatter(maps, cube0 + view * p.cube_stride, vr, px, py, d, w, masked);
+                vr.flush(maps, B.sums());
+            }
+        }
+    };
 
     int64_t done = 0;
     if (VECLOAD) {
-        const uint64_t pol = make_stream_policy();
         const int64_t nvec = p.n / VN;
         for (int64_t i = tid; i < nvec; i += nthreads) {
             T x[VN], y[VN], z[VN], vx[VN], vy[VN], vz[VN], w[VN];
-            unpack<T>(ld_stream(reinterpret_cast<const V*>(X) + i, pol), x);
-            unpack<T>(ld_stream(reinterpret_cast<const V*>(Y) + i, pol), y);
-            unpack<T>(ld_stream(reinterpret_cast<const V*>(VX) + i, pol), vx);
+            Pack<T>::load(X + i * VN, x);
+            Pack<T>::load(Y + i * VN, y);
+            Pack<T>::load(VX + i * VN, vx);
             if (FUSED) {
-                unpack<T>(ld_stream(reinterpret_cast<const V*>(Z) + i, pol), z);
-                unpack<T>(ld_stream(reinterpret_cast<const V*>(VY) + i, pol), vy);
-                unpack<T>(ld_stream(reinterpret_cast<const V*>(VZ) + i, pol), vz);
+                Pack<T>::load(Z + i * VN, z);
+                Pack<T>::load(VY + i * VN, vy);
+                Pack<T>::load(VZ + i * VN, vz);
             }
-            if (W) unpack<T>(ld_stream(reinterpret_cast<const V*>(W) + i, pol), w);
+            if (W) Pack<T>::load(W + i * VN, w);
+            MapRun<ACC> run;
 #pragma unroll
-            for (int k = 0; k < VN; ++k) {
-                const bool m = p.mask_mode != PNM_MASK_NONE && p.mask[i * VN + k] != 0;
-                bin_particle<T, FUSED, ACC>(p, sx, sy, sv, x[k], y[k], FUSED ? z[k] : (T)0, vx[k],
-                                            FUSED ? vy[k] : (T)0, FUSED ? vz[k] : (T)0, W ? w[k] : (T)1, m);
-            }
+            for (int k = 0; k < VN; ++k)
+                one(i * VN + k, x[k], y[k], FUSED ? z[k] : (T)0, vx[k], FUSED ? vy[k] : (T)0, FUSED ? vz[k] : (T)0,
+                    W ? w[k] : (T)1, run);
+            run.flush(maps0, B.sums());
         }
         done = nvec * VN;
     }
     for (int64_t i = done + tid; i < p.n; i += nthreads) {
-        const bool m = p.mask_mode != PNM_MASK_NONE && p.mask[i] != 0;
-        bin_particle<T, FUSED, ACC>(p, sx, sy, sv, X[i], Y[i], FUSED ? Z[i] : (T)0, VX[i],
-                                    FUSED ? VY[i] : (T)0, FUSED ? VZ[i] : (T)0, W ? W[i] : (T)1, m);
+        MapRun<ACC> run;
+        one(i, X[i], Y[i], FUSED ? Z[i] : (T)0, VX[i], FUSED ? VY[i] : (T)0, FUSED ? VZ[i] : (T)0, W ? W[i] : (T)1, run);
+        run.flush(maps0, B.sums());
     }
 }
 

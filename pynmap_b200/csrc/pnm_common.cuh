@@ -53,19 +53,8 @@ __device__ __forceinline__ int find_bin(T x, const T* __restrict__ thr, int n, T
 //   F64   : RED.E.ADD.F64.RN at L2 (round-to-nearest, no flush-to-zero, unlike the f32 RED)
 //   FIXED : RED.E.ADD.64 on rint(value * 2^k): integer addition is associative, so the result
 //           is independent of atomic ordering and of how particles are split over GPUs.
-// atomicAdd with an unused result compiles to REDG (no return trip).
+// atomicAdd with an unused result compiles to REDG (no return trip).  See red_add / to_acc in
+// pnm_bin.cuh.
 // --------------------------------------------------------------------------------------------
-template <int ACC>
-__device__ __forceinline__ void acc_add(void* base, int64_t idx, double value, double scale) {
-    if (ACC == PNM_ACC_F64) {
-        atomicAdd(reinterpret_cast<double*>(base) + idx, value);
-    } else {
-        // non-finite values quantise to 0 in FIXED mode (documented deviation: the float64
-        // path propagates NaN like the reference does)
-        double s = value * scale;
-        long long q = is_finite(s) ? __double2ll_rn(s) : 0ll;
-        atomicAdd(reinterpret_cast<unsigned long long*>(base) + idx, (unsigned long long)q);
-    }
-}
 
 }  // namespace pnm

@@ -189,15 +189,16 @@ int pnm_project_host(int device, int64_t n, int dtype,
 
     const int64_t maps_elems = pnm_maps_acc_elems(grid), cube_elems = pnm_cube_acc_elems(grid);
     const int64_t npix = (int64_t)nx * ny;
-    // arena: [maps acc | cube acc | M V S | smoothing out | smoothing scratch]
-    const size_t arena_bytes = (size_t)(maps_elems + cube_elems + 3 * npix + (smooth ? 2 * cube_elems : 0)) * 8;
+    // arena: [maps acc | cube acc | M V S | cube out | smoothing out | smoothing scratch]
+    const size_t arena_bytes = (size_t)(maps_elems + cube_elems + 3 * npix + cube_elems + (smooth ? 2 * cube_elems : 0)) * 8;
     rc = ensure_ring(device, (size_t)kChunk * 8, arena_bytes);
     if (rc != PNM_OK) { pnm_grid_destroy(grid); return rc; }
     char* arena = static_cast<char*>(g_ring.arena);
     void* acc_maps = arena;
     void* acc_cube = arena + (size_t)maps_elems * 8;
     double* out_maps = reinterpret_cast<double*>(arena + (size_t)(maps_elems + cube_elems) * 8);
-    double* smooth_out = out_maps + 3 * npix;
+    double* cube_out = out_maps + 3 * npix;
+    double* smooth_out = cube_out + cube_elems;
     double* smooth_work = smooth_out + cube_elems;
 
     int sums = 0;
@@ -218,9 +219,8 @@ int pnm_project_host(int device, int64_t n, int dtype,
             if (hosts[k]) e = cudaMemcpyAsync(hosts[k], out_maps + k * npix, (size_t)npix * 8, cudaMemcpyDeviceToHost, s0);
     }
     if (e == cudaSuccess && rc == PNM_OK && want_cube) {
-        rc = pnm_finalize_cube(grid, acc_cube, acc_mode, acc_mode == PNM_ACC_FIXED ? scales3_host[0] : 1.0,
-                               static_cast<double*>(acc_cube), s0);
-        const double* result = static_cast<const double*>(acc_cube);
+        rc = pnm_finalize_cube(grid, acc_cube, acc_mode, acc_mode == PNM_ACC_FIXED ? scales3_host[0] : 1.0, cube_out, s0);
+        const double* result = cube_out;
         if (rc == PNM_OK && smooth) {
             rc = pnm_smooth_cube(result, smooth_out, smooth_work, nx, ny, nv, taps0_host, ntaps0, taps1_host, ntaps1, s0);
             result = smooth_out;

@@ -24,40 +24,55 @@ __global__ void __launch_bounds__(256) k_rotate(const T* __restrict__ x, const T
 }
 
 // ---------------------------------------------------------------- accumulator -> float64
+// maps accumulator: [replica][iy][ix][4]; cube accumulator: [iv][ix][iy] (velocity-major).
 template <int ACC>
-__device__ __forceinline__ double acc_load(const void* base, int64_t idx, double inv_scale) {
-    if (ACC == PNM_ACC_F64) return reinterpret_cast<const double*>(base)[idx];
-    return __dmul_rn((double)reinterpret_cast<const long long*>(base)[idx], inv_scale);
+__device__ __forceinline__ double maps_slot(const void* acc_maps, int64_t npix, int replicas, int pix, int slot,
+                                            double inv_scale) {
+    const int64_t stride = npix * PNM_MAP_SLOTS, at = (int64_t)pix * PNM_MAP_SLOTS + slot;
+    if (ACC == PNM_ACC_F64) {
+        double t = 0.0;
+        for (int r = 0; r < replicas; ++r) t = __dadd_rn(t, reinterpret_cast<const double*>(acc_maps)[r * stride + at]);
+        return t;
+    }
+    long long t = 0;
+    for (int r = 0; r < replicas; ++r) t += reinterpret_cast<const long long*>(acc_maps)[r * stride + at];
+    return __dmul_rn((double)t, inv_scale);
 }
 
-// K5 (grid.py:133-138).  Separate roundings (no FMA contraction) so that equal sums give
-// bit-equal V and S: numpy evaluates s2/s0, V*V and the subtraction as three ufunc calls.
+// K5 (grid.py:133-138).  One thread per spaxel q = ix*ny + iy, so that the V-sum of the cube (needed
+// with PNM_W_FROM_CUBE) is a coalesced column sum.  Separate roundings (no FMA contraction) so
+// that equal sums give bit-equal V and S: numpy evaluates s2/s0, V*V and the subtraction as three
+// ufunc calls.
 template <int ACC>
 __global__ void __launch_bounds__(256) k_finalize_vmaps(const void* acc_maps, const void* acc_cube,
-                                                        int nx, int ny, int nv, int w_from_cube,
+                                                        int nx, int ny, int nv, int replicas, int w_from_cube,
                                                         double is0, double is1, double is2,
                                                         double* M, double* V, double* S, double* S1o, double* S2o) {
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;   // = iy*nx + ix
-    if (pix >= nx * ny) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;     // = ix*ny + iy
+    const int npix = nx * ny;
+    if (q >= npix) return;
+    const int ix = q / ny, iy = q - ix * ny;
+    const int pix = iy * nx + ix;                            // map layout [iy][ix] (the reference's .T)
     double s0;
     if (w_from_cube) {
-        // sum w = particles outside the V range (slot 0) + the V-sum of the cube at [ix][iy][:]
-        const int iy = pix / nx, ix = pix - iy * nx;
-        const int64_t base = ((int64_t)ix * ny + iy) * nv;
+        // sum w = remainder outside the V range (slot 0) + the V-sum of the cube at this spaxel
         if (ACC == PNM_ACC_F64) {
-            double t = reinterpret_cast<const double*>(acc_maps)[(int64_t)pix * PNM_MAP_SLOTS];
-            for (int k = 0; k < nv; ++k) t = __dadd_rn(t, reinterpret_cast<const double*>(acc_cube)[base + k]);
+            double t = maps_slot<ACC>(acc_maps, npix, replicas, pix, 0, 1.0);
+            for (int k = 0; k < nv; ++k) t = __dadd_rn(t, reinterpret_cast<const double*>(acc_cube)[(int64_t)k * npix + q]);
             s0 = t;
         } else {
-            long long t = reinterpret_cast<const long long*>(acc_maps)[(int64_t)pix * PNM_MAP_SLOTS];
-            for (int k = 0; k < nv; ++k) t += reinterpret_cast<const long long*>(acc_cube)[base + k];
+            const int64_t stride = (int64_t)npix * PNM_MAP_SLOTS;
+            long long t = 0;
+            for (int r = 0; r < replicas; ++r)
+                t += reinterpret_cast<const long long*>(acc_maps)[r * stride + (int64_t)pix * PNM_MAP_SLOTS];
+            for (int k = 0; k < nv; ++k) t += reinterpret_cast<const long long*>(acc_cube)[(int64_t)k * npix + q];
             s0 = __dmul_rn((double)t, is0);
         }
     } else {
-        s0 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 0, is0);
+        s0 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 0, is0);
     }
-    const double s1 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 1, is1);
-    const double s2 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 2, is2);
+    const double s1 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 1, is1);
+    const double s2 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 2, is2);
     double v = 0.0, s = 0.0;
     if (s0 != 0.0) {
         v = __ddiv_rn(s1, s0);
@@ -72,21 +87,56 @@ __global__ void __launch_bounds__(256) k_finalize_vmaps(const void* acc_maps, co
 
 // grid.py:203-205
 template <int ACC>
-__global__ void __launch_bounds__(256) k_finalize_map(const void* acc_maps, int npix, double is0, double is1,
-                                                      double* W, double* D, double* DW) {
+__global__ void __launch_bounds__(256) k_finalize_map(const void* acc_maps, int npix, int replicas,
+                                                      double is0, double is1, double* W, double* D, double* DW) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
-    const double s0 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 0, is0);
-    const double s1 = acc_load<ACC>(acc_maps, (int64_t)pix * PNM_MAP_SLOTS + 1, is1);
+    const double s0 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 0, is0);
+    const double s1 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 1, is1);
     if (W) W[pix] = s0;
     if (D) D[pix] = (s0 != 0.0) ? __ddiv_rn(s1, s0) : 0.0;
     if (DW) DW[pix] = s1;
 }
 
-__global__ void __launch_bounds__(256) k_fixed_to_f64(const long long* in, double* out, int64_t n, double inv_scale) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        out[i] = __dmul_rn((double)in[i], inv_scale);
+// fold the map replicas into replica 0 (and clear the others) before a multi-GPU reduce
+template <int ACC>
+__global__ void __launch_bounds__(256) k_fold_maps(void* acc_maps, int64_t per_replica, int replicas) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per_replica) return;
+    if (ACC == PNM_ACC_F64) {
+        double* a = reinterpret_cast<double*>(acc_maps);
+        double t = 0.0;
+        for (int r = 0; r < replicas; ++r) { t = __dadd_rn(t, a[r * per_replica + i]); if (r) a[r * per_replica + i] = 0.0; }
+        a[i] = t;
+    } else {
+        long long* a = reinterpret_cast<long long*>(acc_maps);
+        long long t = 0;
+        for (int r = 0; r < replicas; ++r) { t += a[r * per_replica + i]; if (r) a[r * per_replica + i] = 0; }
+        a[i] = t;
+    }
+}
+
+// cube accumulator [iv][q] -> reference layout [q][iv] = cube[ix][iy][iv] (grid.py:259) as float64:
+// 32x32 shared-memory tile transpose, both sides coalesced.
+template <int ACC>
+__global__ void __launch_bounds__(256) k_cube_out(const void* acc_cube, double* out, int npix, int nv, double inv_scale) {
+    __shared__ double tile[32][33];
+    const int q0 = blockIdx.x * 32, v0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int iv = v0 + r, q = q0 + threadIdx.x;
+        double val = 0.0;
+        if (iv < nv && q < npix) {
+            const int64_t at = (int64_t)iv * npix + q;
+            val = (ACC == PNM_ACC_F64) ? reinterpret_cast<const double*>(acc_cube)[at]
+                                       : __dmul_rn((double)reinterpret_cast<const long long*>(acc_cube)[at], inv_scale);
+        }
+        tile[r][threadIdx.x] = val;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int q = q0 + r, iv = v0 + threadIdx.x;
+        if (q < npix && iv < nv) out[(int64_t)q * nv + iv] = tile[threadIdx.x][r];
+    }
 }
 
 // ---------------------------------------------------------------- K4: separable Gaussian

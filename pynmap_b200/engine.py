@@ -108,6 +108,7 @@ class Grid(object):
         self.edges_y = bin_edges(limXY[2], limXY[3], self.ny)
         self.edges_v = bin_edges(limV[0], limV[1], self.nv) if self.nv else None
         self.handle = ctypes.c_void_p()
+        self._mesh_np = self._mesh_dev = None
         ex, ey = _lib.doubles(self.edges_x), _lib.doubles(self.edges_y)
         ev = _lib.doubles(self.edges_v) if self.nv else None
         with torch.cuda.device(self.device):
@@ -115,6 +116,16 @@ class Grid(object):
 
     @property
     def maps_elems(self):
+        """8-byte elements of one view's (opaque, replicated) maps accumulator."""
+        return int(_lib.load().pnm_maps_acc_elems(self.handle))
+
+    @property
+    def map_replicas(self):
+        return int(_lib.load().pnm_grid_map_replicas(self.handle))
+
+    @property
+    def maps_fold_elems(self):
+        """Elements that carry the sums after fold_maps (the first replica)."""
         return self.nx * self.ny * _lib.MAP_SLOTS
 
     @property
@@ -122,10 +133,23 @@ class Grid(object):
         return self.nx * self.ny * self.nv
 
     def centres(self):
+        """Pixel centres (grid.py:141-142, :247-249); fresh arrays, the caller may keep them."""
         px = np.linspace(self.limXY[0], self.limXY[1], self.nx)
         py = np.linspace(self.limXY[2], self.limXY[3], self.ny)
         pv = np.linspace(self.limV[0], self.limV[1], self.nv) if self.nv else None
         return px, py, pv
+
+    def mesh(self, want_torch):
+        """gridX, gridY of the reference (np.meshgrid of the centres, (nY, nX)).  The device copy is
+        made once per grid: a per-call pageable upload would stall the stream."""
+        if self._mesh_np is None:
+            px, py, _ = self.centres()
+            self._mesh_np = np.meshgrid(px, py)
+        if not want_torch:
+            return self._mesh_np[0].copy(), self._mesh_np[1].copy()
+        if self._mesh_dev is None:
+            self._mesh_dev = tuple(torch.from_numpy(a).to(self.device) for a in self._mesh_np)
+        return self._mesh_dev[0].clone(), self._mesh_dev[1].clone()
 
     def __del__(self):
         try:
@@ -280,13 +304,18 @@ def finalize_map(grid, maps, acc, scales):
 
 
 def finalize_cube(grid, cube, acc, scales):
-    """-> float64 (nX, nY, nV) device tensor (a view of the accumulator in f64 mode)."""
-    shape = (grid.nx, grid.ny, grid.nv)
-    if acc.code == _lib.ACC_F64:
-        return cube.view(shape)
-    out = torch.empty(shape, dtype=torch.float64, device=grid.device)
-    _lib.call("pnm_finalize_cube", grid.handle, ptr(cube), acc.code, float(scales[0]), ptr(out), stream_ptr())
+    """velocity-major accumulator -> float64 (nX, nY, nV) device tensor (np.histogramdd layout)."""
+    out = torch.empty((grid.nx, grid.ny, grid.nv), dtype=torch.float64, device=grid.device)
+    scale = float(scales[0]) if acc.code == _lib.ACC_FIXED else 1.0
+    _lib.call("pnm_finalize_cube", grid.handle, ptr(cube), acc.code, scale, ptr(out), stream_ptr())
     return out
+
+
+def fold_maps(grid, maps, acc):
+    """Sum the map replicas into the first one; returns the view that carries the totals (what a
+    multi-GPU reduction has to move)."""
+    _lib.call("pnm_fold_maps", grid.handle, ptr(maps), acc.code, stream_ptr())
+    return maps[:grid.maps_fold_elems]
 
 
 # ----------------------------------------------------------------------------- smoothing

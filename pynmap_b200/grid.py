@@ -42,11 +42,7 @@ def _scales_for(acc, n, w, d):
 
 
 def _mesh(grid, want_torch):
-    px, py, _ = grid.centres()
-    gx, gy = np.meshgrid(px, py)
-    if want_torch:
-        return torch.from_numpy(gx).to(grid.device), torch.from_numpy(gy).to(grid.device)
-    return gx, gy
+    return grid.mesh(want_torch)
 
 
 def points_2vmaps(x, y, v, weights=None, limXY=[-1, 1, -1, 1], nXY=11, mask=None, accumulate="f64"):

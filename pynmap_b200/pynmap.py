@@ -329,11 +329,7 @@ class snapshot(object):
         return maps, cube
 
     def _mesh(self, grid):
-        px, py, _ = grid.centres()
-        gx, gy = np.meshgrid(px, py)
-        if self.output == "torch":
-            return torch.from_numpy(gx).to(grid.device), torch.from_numpy(gy).to(grid.device)
-        return gx, gy
+        return grid.mesh(self.output == "torch")
 
     @staticmethod
     def _mask_arg(kwargs, mode):
@@ -443,7 +439,7 @@ class snapshot(object):
         scales = self._fixed_scales(acc, w, n_total, reduce_max)
         maps, cube = self._run_fused(grid, w, sums, acc, scales)
         if reducer is not None:
-            keep = reducer(maps, cube)
+            keep = reducer(engine.fold_maps(grid, maps, acc), cube)
             if not keep:
                 return None, None
         M, V, S = (self._out(t) for t in engine.finalize_vmaps(grid, maps, cube, sums, acc, scales))
