@@ -326,7 +326,7 @@ def run_b200(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "cpu_baseline": base,
             "e2e": e2e,
-            "gpu_launches": 4 * args.steps,     # k_project_bin, k_finalize_vmaps, k_smooth_axis<0>, k_smooth_axis<1> per step
+            "gpu_launches": 5 * args.steps,     # k_project_bin, k_finalize_vmaps, k_cube_out, k_smooth_axis<0>, <1> per step
             "clocks": clocks,
         }
         print(json.dumps(line))

@@ -214,7 +214,7 @@ int launch_bin(const pnm::BinParams& p, int acc_mode, cudaStream_t st) {
     const void* ptrs[7] = {p.x, p.y, p.z, p.vx, p.vy, p.vz, p.w};
     for (const void* q : ptrs) aligned = aligned && ((reinterpret_cast<uintptr_t>(q) & 31) == 0);   // 256-bit loads
     const int64_t items = aligned ? (p.n + pnm::Pack<T>::N - 1) / pnm::Pack<T>::N : p.n;
-    const int grid = grid_for(items, 256, env_int("PNM_CTAS_PER_SM", PNM_MINBLOCKS));
+    const int grid = grid_for(items, 256, env_int("PNM_CTAS_PER_SM", pnm::kCtasPerSM));
     // SIMPLE: one view, one matrix, no mask -> matrix in registers, cross-particle run merging
     const bool simple = p.nviews == 1 && p.nchain == 1 && p.mask_mode == PNM_MASK_NONE;
     // hot configurations get the set of sums as a compile-time constant (fused path only)
@@ -320,13 +320,14 @@ int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_
     const int wfc = (sums & PNM_W_FROM_CUBE) ? 1 : 0;
     if (wfc && !acc_cube) return fail(PNM_EINVAL, "pnm_finalize_vmaps: PNM_W_FROM_CUBE without cube");
     const int npix = g->nx * g->ny;
-    const int grid = (npix + 255) / 256;
+    const int grid = (npix + 31) / 32;
+    const dim3 block(32, 8);
     if (acc_mode == PNM_ACC_F64) {
-        pnm::k_finalize_vmaps<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, acc_cube, g->nx, g->ny, g->nv,
+        pnm::k_finalize_vmaps<PNM_ACC_F64><<<grid, block, 0, as_stream(stream)>>>(acc_maps, acc_cube, g->nx, g->ny, g->nv,
                                                                               g->replicas, wfc, 1.0, 1.0, 1.0, M, V, S, S1, S2);
     } else if (acc_mode == PNM_ACC_FIXED) {
         if (!scales3_host) return fail(PNM_EINVAL, "pnm_finalize_vmaps: FIXED mode needs scales");
-        pnm::k_finalize_vmaps<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(
+        pnm::k_finalize_vmaps<PNM_ACC_FIXED><<<grid, block, 0, as_stream(stream)>>>(
             acc_maps, acc_cube, g->nx, g->ny, g->nv, g->replicas, wfc, 1.0 / scales3_host[0], 1.0 / scales3_host[1],
             1.0 / scales3_host[2], M, V, S, S1, S2);
     } else {

@@ -2,6 +2,7 @@
 // plus the materialising rotation (K1) and the abs-max reduction used to size fixed-point scales.
 #pragma once
 #include "pnm_common.cuh"
+#include "pnm_bin.cuh"
 
 namespace pnm {
 
@@ -39,8 +40,9 @@ __device__ __forceinline__ double maps_slot(const void* acc_maps, int64_t npix, 
     return __dmul_rn((double)t, inv_scale);
 }
 
-// K5 (grid.py:133-138).  One thread per spaxel q = ix*ny + iy, so that the V-sum of the cube (needed
-// with PNM_W_FROM_CUBE) is a coalesced column sum.  Separate roundings (no FMA contraction) so
+// K5 (grid.py:133-138).  Block = 32 spaxels (q = ix*ny + iy) x 8 velocity slabs: with
+// PNM_W_FROM_CUBE the V-sum of the cube is a coalesced column sum split over the 8 slabs and
+// combined in a fixed order through shared memory.  Separate roundings (no FMA contraction) so
 // that equal sums give bit-equal V and S: numpy evaluates s2/s0, V*V and the subtraction as three
 // ufunc calls.
 template <int ACC>
@@ -48,26 +50,29 @@ __global__ void __launch_bounds__(256) k_finalize_vmaps(const void* acc_maps, co
                                                         int nx, int ny, int nv, int replicas, int w_from_cube,
                                                         double is0, double is1, double is2,
                                                         double* M, double* V, double* S, double* S1o, double* S2o) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;     // = ix*ny + iy
+    using A = typename AccT<ACC>::type;
+    __shared__ A part[8][32];
+    const int q = blockIdx.x * 32 + threadIdx.x;             // = ix*ny + iy
     const int npix = nx * ny;
-    if (q >= npix) return;
+    A t = 0;
+    if (w_from_cube && q < npix) {
+        const A* c = reinterpret_cast<const A*>(acc_cube);
+        for (int k = threadIdx.y; k < nv; k += 8) t += c[(int64_t)k * npix + q];
+    }
+    part[threadIdx.y][threadIdx.x] = t;
+    __syncthreads();
+    if (threadIdx.y != 0 || q >= npix) return;
     const int ix = q / ny, iy = q - ix * ny;
     const int pix = iy * nx + ix;                            // map layout [iy][ix] (the reference's .T)
     double s0;
     if (w_from_cube) {
-        // sum w = remainder outside the V range (slot 0) + the V-sum of the cube at this spaxel
-        if (ACC == PNM_ACC_F64) {
-            double t = maps_slot<ACC>(acc_maps, npix, replicas, pix, 0, 1.0);
-            for (int k = 0; k < nv; ++k) t = __dadd_rn(t, reinterpret_cast<const double*>(acc_cube)[(int64_t)k * npix + q]);
-            s0 = t;
-        } else {
-            const int64_t stride = (int64_t)npix * PNM_MAP_SLOTS;
-            long long t = 0;
-            for (int r = 0; r < replicas; ++r)
-                t += reinterpret_cast<const long long*>(acc_maps)[r * stride + (int64_t)pix * PNM_MAP_SLOTS];
-            for (int k = 0; k < nv; ++k) t += reinterpret_cast<const long long*>(acc_cube)[(int64_t)k * npix + q];
-            s0 = __dmul_rn((double)t, is0);
-        }
+        // sum w = remainder outside the V range (slot 0 of every replica) + the V-sum of the cube
+        const A* m = reinterpret_cast<const A*>(acc_maps);
+        const int64_t stride = (int64_t)npix * PNM_MAP_SLOTS;
+        A tot = 0;
+        for (int r = 0; r < replicas; ++r) tot += m[r * stride + (int64_t)pix * PNM_MAP_SLOTS];
+        for (int k = 0; k < 8; ++k) tot += part[k][threadIdx.x];
+        s0 = (ACC == PNM_ACC_F64) ? (double)tot : __dmul_rn((double)tot, is0);
     } else {
         s0 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 0, is0);
     }
@@ -148,18 +153,32 @@ struct Taps { double t[PNM_MAX_TAPS]; int n; };
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_smooth_axis(const double* __restrict__ in, double* __restrict__ out,
                                                      int nx, int ny, int nv, const __grid_constant__ Taps taps) {
-    const int64_t total = (int64_t)nx * ny * nv;
+    // (the cube has < 2^31 voxels: checked at grid creation, so 32-bit indices are enough)
+    const int total = nx * ny * nv;
     const int r = taps.n / 2;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int64_t plane = i / nv;                  // ix*ny + iy
-        const int ix = (int)(plane / ny), iy = (int)(plane - (int64_t)ix * ny);
+    const int step = AXIS == 0 ? ny * nv : nv;
+    const int len = AXIS == 0 ? nx : ny;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int plane = i / nv;                      // ix*ny + iy
+        const int ix = plane / ny, iy = plane - ix * ny;
         const int pos = AXIS == 0 ? ix : iy;
-        const int len = AXIS == 0 ? nx : ny;
-        const int64_t step = AXIS == 0 ? (int64_t)ny * nv : (int64_t)nv;
         const int lo = max(0, r - pos), hi = min(taps.n - 1, r + (len - 1 - pos));
+        const double* src = in + (i - r * step);
         double acc = 0.0;
-        for (int t = lo; t <= hi; ++t) acc = __fma_rn(taps.t[t], in[i + (int64_t)(t - r) * step], acc);
+        // batches of 8 independent loads (out-of-range taps read a clamped address with weight 0):
+        // the naive dependent loop was latency bound at ~60 us per pass, this one is L2-bandwidth bound
+        for (int t0 = lo; t0 <= hi; t0 += 8) {
+            double v[8], c[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int t = min(t0 + u, hi);
+                v[u] = src[t * step];
+                c[u] = (t0 + u <= hi) ? taps.t[t] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = __fma_rn(c[u], v[u], acc);
+        }
         out[i] = acc;
     }
 }
