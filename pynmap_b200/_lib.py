@@ -54,6 +54,7 @@ _SIGNATURES = {
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
 _lib = None
+_device_ok = False
 
 
 class PnmError(RuntimeError):
@@ -92,9 +93,12 @@ def call(name, *args):
 
 def require_device():
     """Fail loudly when the CUDA path cannot run (no silent CPU path exists)."""
+    global _device_ok
     lib = load()
-    if lib.pnm_device_count() < 1:
-        raise PnmError("no usable sm_100 (B200) device: pynmap_b200 has no CPU fallback")
+    if not _device_ok:
+        if lib.pnm_device_count() < 1:
+            raise PnmError("no usable sm_100 (B200) device: pynmap_b200 has no CPU fallback")
+        _device_ok = True        # checked once per process: the query costs microseconds per call
     return lib
 
 

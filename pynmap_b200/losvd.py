@@ -110,7 +110,7 @@ class LOSVD(object):
             ecube, e_torch = self._cube_on_device(self.err_losvd)
             closvd.err_losvd = engine.to_output(engine.smooth_cube(ecube, taps_axis0, taps_axis1), e_torch)
         else:
-            closvd.err_losvd = copy.deepcopy(self.err_losvd)
+            closvd.err_losvd = self.err_losvd.copy()     # (nX, nY) array of None: nothing deep to copy
 
         closvd.fwhmx = reached_fwhmx
         closvd.fwhmy = reached_fwhmy

@@ -439,7 +439,8 @@ class snapshot(object):
         scales = self._fixed_scales(acc, w, n_total, reduce_max)
         maps, cube = self._run_fused(grid, w, sums, acc, scales)
         if reducer is not None:
-            keep = reducer(engine.fold_maps(grid, maps, acc), cube)
+            engine.fold_maps(grid, maps, acc)
+            keep = reducer(*engine.reduce_span(grid, maps, cube))
             if not keep:
                 return None, None
         M, V, S = (self._out(t) for t in engine.finalize_vmaps(grid, maps, cube, sums, acc, scales))
