@@ -209,14 +209,17 @@ namespace {
 
 template <typename T, bool FUSED>
 int launch_bin(const pnm::BinParams& p, int acc_mode, cudaStream_t st) {
-    const size_t smem = (size_t)((p.nx + 1) + (p.ny + 1) + (p.nv + 1)) * sizeof(T);
     bool aligned = true;
     const void* ptrs[7] = {p.x, p.y, p.z, p.vx, p.vy, p.vz, p.w};
     for (const void* q : ptrs) aligned = aligned && ((reinterpret_cast<uintptr_t>(q) & 31) == 0);   // 256-bit loads
     const int64_t items = aligned ? (p.n + pnm::Pack<T>::N - 1) / pnm::Pack<T>::N : p.n;
-    const int grid = grid_for(items, 256, env_int("PNM_CTAS_PER_SM", pnm::kCtasPerSM));
-    // SIMPLE: one view, one matrix, no mask -> matrix in registers, cross-particle run merging
+    const int grid = grid_for(items, pnm::kBinThreads, env_int("PNM_CTAS_PER_SM", pnm::kCtasPerSM));
+    // SIMPLE: one view, one matrix, no mask -> matrix in registers, cross-particle run merging, hybrid scatter
     const bool simple = p.nviews == 1 && p.nchain == 1 && p.mask_mode == PNM_MASK_NONE;
+    // shared memory: edge tables (+ the TMA staging area when the hybrid scatter can run)
+    size_t smem = pnm::bin_table_bytes<T>(p.nx, p.ny, p.nv);
+    if (aligned && simple && p.tma_slots > 0) smem += pnm::bin_stage_bytes(pnm::kBinThreads);
+    if (smem > 227 * 1024) return fail(PNM_ELIMIT, "k_project_bin: %zu bytes of shared memory", smem);
     // hot configurations get the set of sums as a compile-time constant (fused path only)
     constexpr int kFull = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2 | PNM_SUM_CUBE | PNM_W_FROM_CUBE;
     constexpr int kMaps = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2;
@@ -283,6 +286,9 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     p.sums = sums; p.nchain = fused ? nchain : 1; p.nviews = fused ? nviews : 1;
     p.replicas = g->replicas;
     p.rep_shift = env_int("PNM_REP_SHIFT", 5);
+    // hybrid scatter: 16-byte TMA bulk reductions need a 16-byte aligned maps accumulator
+    p.tma_slots = (acc_maps && (reinterpret_cast<uintptr_t>(acc_maps) & 15) == 0)
+                      ? std::max(0, std::min(env_int("PNM_TMA_SLOTS", pnm::kTmaSlots), pnm::kTmaSlots)) : 0;
     for (int k = 0; k < 3; ++k) p.scale[k] = (acc_mode == PNM_ACC_FIXED) ? scales3_host[k] : 1.0;
     p.acc_maps = acc_maps; p.acc_cube = acc_cube;
     p.maps_stride = pnm_maps_acc_elems(g); p.cube_stride = pnm_cube_acc_elems(g);
@@ -398,6 +404,7 @@ int pnm_smooth_cube(const double* cube_in, double* cube_out, double* work, int32
     t1.n = ntaps1; memcpy(t1.t, taps1_host, sizeof(double) * ntaps1);
     const int64_t total = (int64_t)nx * ny * nv;
     const int grid = grid_for(total, 256, 8);
+    // one thread per kSmoothOut outputs along the convolved axis
     pnm::k_smooth_axis<0><<<grid, 256, 0, as_stream(stream)>>>(cube_in, work, nx, ny, nv, t0);
     pnm::k_smooth_axis<1><<<grid, 256, 0, as_stream(stream)>>>(work, cube_out, nx, ny, nv, t1);
     PNM_CUDA(cudaGetLastError());

@@ -1,24 +1,29 @@
 // pnm_bin.cuh -- fused rotate + project + bin kernel (K1+K2+K3 of SURVEY.md 2.2).
 //
 // One pass over the SoA particle arrays produces, per viewing angle, the (opaque) accumulators
-//   maps  [view][replica][iy][ix][4] = { sum w (or its out-of-V-range remainder), sum w*d, sum w*d*d, - }
+//   maps  [view][replica][iy][ix][4] = { sum w*d, sum w*d*d, sum w (or its out-of-V remainder), - }
 //   cube  [view][iv][ix][iy]         =   sum w
 // which pnm_finalize_* turn into the reference's layouts.  Reference semantics:
 // rotation.py:115-117 (rotation), grid.py:121-131 / :200-201 (2-D moment histograms),
 // grid.py:252-259 (3-D histogram).
 //
 // Roofline: HBM (28 B per float32 particle).  What actually bounds the kernel is the SM's
-// reduction-issue rate (~1.3 clk per scattered RED lane, measured), so the design minimises REDs
-// per particle, keeps the instruction stream short and spreads same-address traffic:
-//   * accumulators (<= 34 MB for 128x128x256) stay resident in the 126 MB L2; the particle stream
+// reduction-issue rate (0.77 scattered RED lanes per clock per SM, measured), so the design
+// minimises REDs per particle, keeps the instruction stream short and spreads same-address traffic:
+//   * accumulators (<= 66 MB for 128x128x256) stay resident in the 126 MB L2; the particle stream
 //     is loaded with 256-bit LDG, no L1 allocation and an L2 evict-first policy;
 //   * maps are replicated R times (one replica per warp id) so that the galaxy-centre pixels, which
 //     receive ~2 % of all particles, do not serialise on one L2 sector;
 //   * the cube is stored velocity-major, which spreads the hot central spaxel over ~nv L2 lines
 //     instead of one 2 KB column;
 //   * consecutive particles of a thread that fall in the same pixel are merged in registers before
-//     the RED (free for random order, ~1 RED per run for space-filling-curve ordered snapshots);
+//     the reduction (free for random order, ~1 per run for space-filling-curve ordered snapshots);
 //   * with PNM_W_FROM_CUBE the map's sum w costs no RED at all for particles inside the V range;
+//   * HYBRID SCATTER: (sum w*d, sum w*d*d) sit in one 16-byte half sector, so most map updates are
+//     staged in shared memory and sent as ONE 16-byte TMA bulk reduction
+//     (cp.reduce.async.bulk.global.shared::cta ... add.f64/.u64, SASS UBLKRED) instead of two LSU
+//     REDs.  The TMA unit sustains ~7.5e10 such ops/s per GPU next to the LSU's 1.9e11 REDs/s and
+//     the two overlap (scripts/tma_mix_bench.cu: 1.60 -> 1.21 ms per 1e8 particles at a 3:1 split);
 //   * bin lookup: the uniform guess floor((x-x0)*inv) is PROVABLY the numpy bin whenever its
 //     fractional part is further than `eps` from an integer (eps bounds the float rounding of the
 //     guess plus the deviation of np.linspace edges from an affine grid, computed at grid
@@ -43,6 +48,7 @@ struct BinParams {
     int nchain, nviews;
     int replicas;                                     // power of two
     int rep_shift;                                    // replica = (thread id >> rep_shift) & (replicas-1)
+    int tma_slots;                                    // map updates per tile sent through the TMA unit (0..kTmaSlots)
     double scale[3];
     void* acc_maps; void* acc_cube;
     int64_t maps_stride, cube_stride;                 // 8-byte elements per view (maps: all replicas)
@@ -125,6 +131,58 @@ __device__ __forceinline__ void red_add(long long* p, long long v) {
     atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)v);
 }
 
+// ---- TMA staging of (S1, S2) pairs ---------------------------------------------------------------
+// Shared-memory layout per CTA: kTmaStages x kTmaSlots x blockDim.x records of 16 bytes (conflict
+// free: consecutive threads, consecutive records) + the matching destination offsets.  A thread
+// only ever touches its own records, so ordering needs no CTA barrier: generic-proxy writes ->
+// fence.proxy.async -> bulk reductions -> commit_group; before a stage is rewritten two tiles
+// later, wait_group.read 1 guarantees the TMA unit has read it.
+// of the (up to) 8 map updates of a tile; the rest take the LSU path.  Measured on the bench
+// workload (1e8 particles, maps + cube): 0 -> 1.78 ms, 2 -> 1.65, 4 -> 1.59, 5 -> 1.67, 6 -> 1.82
+constexpr int kTmaSlots = 4;
+constexpr int kTmaStages = 2;
+
+__device__ __forceinline__ void tma_fence_writes() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_reduce16(double* dst, const void* src_smem) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 16;"
+                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)) : "memory");
+}
+__device__ __forceinline__ void tma_reduce16(long long* dst, const void* src_smem) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;"
+                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)) : "memory");
+}
+
+template <int ACC>
+struct TmaStage {
+    using A = typename AccT<ACC>::type;
+    A* vals;        // this thread's record 0 of the current stage (record k at vals + 2*k*stride)
+    int* offs;      // destination offsets, same indexing (offs + k*stride)
+    int stride;     // blockDim.x
+    int used, cap;  // records filled in this tile, capacity (0 disables the TMA path)
+
+    __device__ __forceinline__ bool push(int off, A s1, A s2) {
+        if (used >= cap) return false;
+        A* rec = vals + 2 * used * stride;
+        rec[0] = s1; rec[1] = s2;                       // one STS.128
+        offs[used * stride] = off;
+        ++used;
+        return true;
+    }
+    // end of tile: hand the records to the TMA unit
+    __device__ __forceinline__ void drain(A* maps) {
+        if (cap == 0) return;
+        if (used > 0) {
+            tma_fence_writes();
+            for (int k = 0; k < used; ++k) tma_reduce16(maps + offs[k * stride] + kSlotS1, vals + 2 * k * stride);
+        }
+        tma_commit();                                   // (possibly empty) group: keeps the group count in step
+        used = 0;
+    }
+};
+
 // pending run of map contributions that share one pixel (merged in registers)
 template <int ACC>
 struct MapRun {
@@ -133,16 +191,19 @@ struct MapRun {
     A s0 = 0, s1 = 0, s2 = 0;
     bool has0 = false;
 
-    __device__ __forceinline__ void flush(A* maps, int sums) {
+    __device__ __forceinline__ void flush(A* maps, int sums, TmaStage<ACC>& st) {
         if (off < 0) return;
-        if ((sums & PNM_SUM_W) && has0) red_add(maps + off, s0);
-        if (sums & PNM_SUM_WD) red_add(maps + off + 1, s1);
-        if (sums & PNM_SUM_WD2) red_add(maps + off + 2, s2);
+        if ((sums & PNM_SUM_W) && has0) red_add(maps + off + kSlotS0, s0);
+        const bool both = (sums & PNM_SUM_WD) && (sums & PNM_SUM_WD2);
+        if (!(both && st.push(off, s1, s2))) {
+            if (sums & PNM_SUM_WD) red_add(maps + off + kSlotS1, s1);
+            if (sums & PNM_SUM_WD2) red_add(maps + off + kSlotS2, s2);
+        }
         off = -1;
     }
-    __device__ __forceinline__ void add(A* maps, int sums, int o, bool use0, A a0, A a1, A a2) {
+    __device__ __forceinline__ void add(A* maps, int sums, TmaStage<ACC>& st, int o, bool use0, A a0, A a1, A a2) {
         if (o != off) {
-            flush(maps, sums);
+            flush(maps, sums, st);
             off = o; s0 = 0; s1 = a1; s2 = a2; has0 = false;
         } else {
             s1 += a1; s2 += a2;
@@ -169,37 +230,9 @@ struct Binner {
     }
     __device__ __forceinline__ int sums() const { return SUMS >= 0 ? SUMS : rsums; }
 
-    // bins only: off = map slot offset (or -1: particle dropped), vox = cube offset (or -1: outside V)
-    __device__ __forceinline__ void locate(T px, T py, T d, int& off, int& vox) {
-        const int sm = sums();
-        const bool want_v = (sm & PNM_SUM_CUBE) != 0;
-        bool sure = true;
-        int ix = guess_bin<T>(px, ax, sure);
-        int iy = guess_bin<T>(py, ay, sure);
-        int iv = want_v ? guess_bin<T>(d, av, sure) : -1;
-        if (!sure) {                                     // ~1e-3 of the particles
-            ix = exact_bin<T>(px, ax.thr, ax.n);
-            iy = exact_bin<T>(py, ay.thr, ay.n);
-            if (want_v) iv = exact_bin<T>(d, av.thr, av.n);
-        }
-        const bool in_xy = (unsigned)ix < (unsigned)nx && (unsigned)iy < (unsigned)ny;
-        off = in_xy ? (iy * nx + ix) * PNM_MAP_SLOTS : -1;
-        vox = (in_xy && want_v && (unsigned)iv < (unsigned)av.n) ? iv * npix + ix * ny + iy : -1;
-    }
-    // the reductions of one located particle
-    __device__ __forceinline__ void emit(A* maps, A* cube, MapRun<ACC>& run, int off, int vox, T w, T d) {
-        if (off < 0) return;
-        const int sm = sums();
-        if (sm & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2)) {
-            const bool use0 = (sm & PNM_SUM_W) && !((sm & PNM_W_FROM_CUBE) && vox >= 0);
-            run.add(maps, sm, off, use0, to_acc<ACC>(w, sc0), to_acc<ACC>(mul_rn(w, d), sc1),
-                    to_acc<ACC>(mul_rn(w, mul_rn(d, d)), sc2));
-        }
-        if (vox >= 0) red_add(cube + vox, to_acc<ACC>(w, sc0));
-    }
-
-    // (px, py, d) already projected
-    __device__ __forceinline__ void scatter(A* maps, A* cube, MapRun<ACC>& run, T px, T py, T d, T w, bool masked_in) {
+    // (px, py, d) already projected: locate the bins, then reduce
+    __device__ __forceinline__ void scatter(A* maps, A* cube, MapRun<ACC>& run, TmaStage<ACC>& st,
+                                            T px, T py, T d, T w, bool masked_in) {
         if (masked_in) {
             if (mask_mode == PNM_MASK_PLAIN) return;
             if (mask_mode == PNM_MASK_AND_NONFINITE && !is_finite(d)) return;
@@ -219,8 +252,8 @@ struct Binner {
         const bool in_v = want_v && (unsigned)iv < (unsigned)av.n;
         if (sm & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2)) {
             const bool use0 = (sm & PNM_SUM_W) && !((sm & PNM_W_FROM_CUBE) && in_v);
-            run.add(maps, sm, (iy * nx + ix) * PNM_MAP_SLOTS, use0, to_acc<ACC>(w, sc0), to_acc<ACC>(mul_rn(w, d), sc1),
-                    to_acc<ACC>(mul_rn(w, mul_rn(d, d)), sc2));
+            run.add(maps, sm, st, (iy * nx + ix) * PNM_MAP_SLOTS, use0, to_acc<ACC>(w, sc0),
+                    to_acc<ACC>(mul_rn(w, d), sc1), to_acc<ACC>(mul_rn(w, mul_rn(d, d)), sc2));
         }
         if (in_v) red_add(cube + (iv * npix + ix * ny + iy), to_acc<ACC>(w, sc0));
     }
@@ -245,10 +278,6 @@ __device__ __forceinline__ void project_chain(const float* m, int nchain, T x, T
     px = ax; py = ay;
 }
 
-// ---- kernel: persistent grid-stride loop; each thread takes Pack<T>::N consecutive particles per
-// array with one 256-bit load (VECLOAD), scalar path for the tail and for unaligned pointers.
-// SIMPLE = one view, one matrix, no mask: the matrix lives in registers and consecutive particles
-// of a thread merge their map contributions. ---------------------------------------------------
 // Grid: far more CTAs than resident slots (kCtasPerSM per SM, 2 resident).  Measured on 10^8
 // particles: 1.98 ms with a grid of exactly the resident CTAs, 1.69 ms with 32 per SM -- SMs differ
 // in their distance to the L2 slices that hold the hot pixels, and the block scheduler balances
@@ -257,8 +286,23 @@ __device__ __forceinline__ void project_chain(const float* m, int nchain, T x, T
 #define PNM_MINBLOCKS 2
 #endif
 constexpr int kCtasPerSM = 32;
+constexpr int kBinThreads = 256;
+
+// dynamic shared memory of k_project_bin: edge tables, then (SIMPLE only) the TMA staging area
+template <typename T>
+__host__ __device__ inline size_t bin_table_bytes(int nx, int ny, int nv) {
+    return (((size_t)(nx + 1) + (ny + 1) + (nv + 1)) * sizeof(T) + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t bin_stage_bytes(int threads) {
+    return (size_t)kTmaStages * kTmaSlots * threads * (16 + 4);
+}
+
+// ---- kernel: persistent grid-stride loop; each thread takes Pack<T>::N consecutive particles per
+// array with one 256-bit load (VECLOAD), scalar path for the tail and for unaligned pointers.
+// SIMPLE = one view, one matrix, no mask: the matrix lives in registers, consecutive particles of a
+// thread merge their map contributions and the hybrid LSU/TMA scatter is active. ----------------
 template <typename T, bool FUSED, int ACC, bool VECLOAD, bool SIMPLE, int SUMS>
-__global__ void __launch_bounds__(256, PNM_MINBLOCKS) k_project_bin(const __grid_constant__ BinParams p) {
+__global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(const __grid_constant__ BinParams p) {
     using A = typename AccT<ACC>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sx = reinterpret_cast<T*>(smem_raw);
@@ -286,6 +330,16 @@ __global__ void __launch_bounds__(256, PNM_MINBLOCKS) k_project_bin(const __grid
 #pragma unroll
     for (int k = 0; k < 9; ++k) m[k] = p.mats[k];
 
+    // TMA staging (SIMPLE + vector path only): [stage][slot][thread] records, then the offsets
+    unsigned char* stage_raw = smem_raw + bin_table_bytes<T>(p.nx, p.ny, p.nv);
+    A* const stage_vals = reinterpret_cast<A*>(stage_raw);
+    int* const stage_offs = reinterpret_cast<int*>(stage_raw + (size_t)kTmaStages * kTmaSlots * blockDim.x * 16);
+    TmaStage<ACC> st;
+    st.stride = blockDim.x; st.used = 0;
+    st.cap = (SIMPLE && VECLOAD) ? p.tma_slots : 0;
+    st.vals = stage_vals + 2 * threadIdx.x;
+    st.offs = stage_offs + threadIdx.x;
+
     auto one = [&](int64_t idx, T x, T y, T z, T vx, T vy, T vz, T w, MapRun<ACC>& run) {
         if (SIMPLE) {
             T px = x, py = y, d = vx;
@@ -294,7 +348,7 @@ __global__ void __launch_bounds__(256, PNM_MINBLOCKS) k_project_bin(const __grid
                 py = rot_row(m[3], m[4], m[5], x, y, z);
                 d = rot_row(m[6], m[7], m[8], vx, vy, vz);
             }
-            B.scatter(maps0, cube0, run, px, py, d, w, false);
+            B.scatter(maps0, cube0, run, st, px, py, d, w, false);
         } else {
             const bool masked = p.mask_mode != PNM_MASK_NONE && p.mask[idx] != 0;
             for (int view = 0; view < p.nviews; ++view) {
@@ -302,8 +356,8 @@ __global__ void __launch_bounds__(256, PNM_MINBLOCKS) k_project_bin(const __grid
                 if (FUSED) project_chain<T>(p.mats + (size_t)view * p.nchain * 9, p.nchain, x, y, z, vx, vy, vz, px, py, d);
                 MapRun<ACC> vr;       // no cross-particle merging in the general path
                 A* maps = maps0 + view * p.maps_stride;
-                B.scatter(maps, cube0 + view * p.cube_stride, vr, px, py, d, w, masked);
-                vr.flush(maps, B.sums());
+                B.scatter(maps, cube0 + view * p.cube_stride, vr, st, px, py, d, w, masked);
+                vr.flush(maps, B.sums(), st);
             }
         }
     };
@@ -311,6 +365,7 @@ __global__ void __launch_bounds__(256, PNM_MINBLOCKS) k_project_bin(const __grid
     int64_t done = 0;
     if (VECLOAD) {
         const int64_t nvec = p.n / VN;
+        int parity = 0;
         for (int64_t i = tid; i < nvec; i += nthreads) {
             T x[VN], y[VN], z[VN], vx[VN], vy[VN], vz[VN], w[VN];
             Pack<T>::load(X + i * VN, x);
@@ -322,19 +377,27 @@ __global__ void __launch_bounds__(256, PNM_MINBLOCKS) k_project_bin(const __grid
                 Pack<T>::load(VZ + i * VN, vz);
             }
             if (W) Pack<T>::load(W + i * VN, w);
+            if (st.cap) {                                   // the stage used two tiles ago must have been read
+                tma_wait_read_1();
+                st.vals = stage_vals + ((size_t)parity * kTmaSlots * blockDim.x + threadIdx.x) * 2;
+                st.offs = stage_offs + (size_t)parity * kTmaSlots * blockDim.x + threadIdx.x;
+                parity ^= 1;
+            }
             MapRun<ACC> run;
 #pragma unroll
             for (int k = 0; k < VN; ++k)
                 one(i * VN + k, x[k], y[k], FUSED ? z[k] : (T)0, vx[k], FUSED ? vy[k] : (T)0, FUSED ? vz[k] : (T)0,
                     W ? w[k] : (T)1, run);
-            run.flush(maps0, B.sums());
+            run.flush(maps0, B.sums(), st);
+            st.drain(maps0);
         }
         done = nvec * VN;
+        if (st.cap) { tma_wait_all(); st.cap = 0; }         // every bulk reduction has landed before the kernel ends
     }
     for (int64_t i = done + tid; i < p.n; i += nthreads) {
         MapRun<ACC> run;
         one(i, X[i], Y[i], FUSED ? Z[i] : (T)0, VX[i], FUSED ? VY[i] : (T)0, FUSED ? VZ[i] : (T)0, W ? W[i] : (T)1, run);
-        run.flush(maps0, B.sums());
+        run.flush(maps0, B.sums(), st);
     }
 }
 

@@ -10,6 +10,12 @@ namespace pnm {
 constexpr int kNumSMs = 148;       // B200: 2 dies x 74 SMs
 constexpr int kMaxMats = 64;       // nviews * nchain matrices carried in kernel parameters
 
+// Slot order inside a 32-byte map record.  (S1, S2) share the first, 16-byte aligned half so that
+// one 16-byte TMA bulk reduction updates both; S0 is touched rarely when the cube carries sum w.
+constexpr int kSlotS1 = 0;         // sum w*d
+constexpr int kSlotS2 = 1;         // sum w*d*d
+constexpr int kSlotS0 = 2;         // sum w (or its out-of-V-range remainder)
+
 // --------------------------------------------------------------------------------------------
 // Rotation arithmetic.  np.dot(mat(3x3, f32), pos.T(3xN)) in the reference (rotation.py:115-117)
 // rounds each output as a forward FMA chain over k = 0,1,2 (SURVEY.md 8c KAT 7).  Explicit

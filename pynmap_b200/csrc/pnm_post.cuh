@@ -70,14 +70,14 @@ __global__ void __launch_bounds__(256) k_finalize_vmaps(const void* acc_maps, co
         const A* m = reinterpret_cast<const A*>(acc_maps);
         const int64_t stride = (int64_t)npix * PNM_MAP_SLOTS;
         A tot = 0;
-        for (int r = 0; r < replicas; ++r) tot += m[r * stride + (int64_t)pix * PNM_MAP_SLOTS];
+        for (int r = 0; r < replicas; ++r) tot += m[r * stride + (int64_t)pix * PNM_MAP_SLOTS + kSlotS0];
         for (int k = 0; k < 8; ++k) tot += part[k][threadIdx.x];
         s0 = (ACC == PNM_ACC_F64) ? (double)tot : __dmul_rn((double)tot, is0);
     } else {
-        s0 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 0, is0);
+        s0 = maps_slot<ACC>(acc_maps, npix, replicas, pix, kSlotS0, is0);
     }
-    const double s1 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 1, is1);
-    const double s2 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 2, is2);
+    const double s1 = maps_slot<ACC>(acc_maps, npix, replicas, pix, kSlotS1, is1);
+    const double s2 = maps_slot<ACC>(acc_maps, npix, replicas, pix, kSlotS2, is2);
     double v = 0.0, s = 0.0;
     if (s0 != 0.0) {
         v = __ddiv_rn(s1, s0);
@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(256) k_finalize_map(const void* acc_maps, int 
                                                       double is0, double is1, double* W, double* D, double* DW) {
     const int pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix >= npix) return;
-    const double s0 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 0, is0);
-    const double s1 = maps_slot<ACC>(acc_maps, npix, replicas, pix, 1, is1);
+    const double s0 = maps_slot<ACC>(acc_maps, npix, replicas, pix, kSlotS0, is0);
+    const double s1 = maps_slot<ACC>(acc_maps, npix, replicas, pix, kSlotS1, is1);
     if (W) W[pix] = s0;
     if (D) D[pix] = (s0 != 0.0) ? __ddiv_rn(s1, s0) : 0.0;
     if (DW) DW[pix] = s1;
@@ -150,36 +150,42 @@ __global__ void __launch_bounds__(256) k_cube_out(const void* acc_cube, double* 
 // Threads run along iv so every tap is a coalesced row read served by L2 (the cube is resident).
 struct Taps { double t[PNM_MAX_TAPS]; int n; };
 
+// Each thread produces kSmoothOut consecutive outputs along AXIS from one sliding window of inputs:
+// ntaps + 3 loads for 4 outputs instead of 4 * ntaps (the pass is bound by L2 -> SM traffic), one
+// load + 4 FMAs per tap.  Every output is the same ordered sum_t fma(taps[t], in[..], acc) as a
+// one-output-per-thread loop would compute; zero fill = out-of-range loads return 0.
+constexpr int kSmoothOut = 4;
+
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_smooth_axis(const double* __restrict__ in, double* __restrict__ out,
                                                      int nx, int ny, int nv, const __grid_constant__ Taps taps) {
     // (the cube has < 2^31 voxels: checked at grid creation, so 32-bit indices are enough)
-    const int total = nx * ny * nv;
-    const int r = taps.n / 2;
-    const int step = AXIS == 0 ? ny * nv : nv;
     const int len = AXIS == 0 ? nx : ny;
+    const int nblk = (len + kSmoothOut - 1) / kSmoothOut;
+    const int items = (AXIS == 0 ? nblk * ny : nx * nblk) * nv;
+    const int step = AXIS == 0 ? ny * nv : nv;
+    const int r = taps.n / 2;
     const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int plane = i / nv;                      // ix*ny + iy
-        const int ix = plane / ny, iy = plane - ix * ny;
-        const int pos = AXIS == 0 ? ix : iy;
-        const int lo = max(0, r - pos), hi = min(taps.n - 1, r + (len - 1 - pos));
-        const double* src = in + (i - r * step);
-        double acc = 0.0;
-        // batches of 8 independent loads (out-of-range taps read a clamped address with weight 0):
-        // the naive dependent loop was latency bound at ~60 us per pass, this one is L2-bandwidth bound
-        for (int t0 = lo; t0 <= hi; t0 += 8) {
-            double v[8], c[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int t = min(t0 + u, hi);
-                v[u] = src[t * step];
-                c[u] = (t0 + u <= hi) ? taps.t[t] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc = __fma_rn(c[u], v[u], acc);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
+        const int iv = i % nv, rest = i / nv;
+        int pos0, base;                                 // first output position along AXIS, its flat index
+        if (AXIS == 0) { const int iy = rest % ny; pos0 = (rest / ny) * kSmoothOut; base = (pos0 * ny + iy) * nv + iv; }
+        else { const int b = rest % nblk; const int ix = rest / nblk; pos0 = b * kSmoothOut; base = (ix * ny + pos0) * nv + iv; }
+        auto at = [&](int p) -> double { return (p >= 0 && p < len) ? in[base + (p - pos0) * step] : 0.0; };
+        double acc[kSmoothOut] = {0.0, 0.0, 0.0, 0.0};
+        double w0 = at(pos0 - r), w1 = at(pos0 - r + 1), w2 = at(pos0 - r + 2), w3 = at(pos0 - r + 3);
+        for (int t = 0; t < taps.n; ++t) {
+            const double c = taps.t[t];
+            acc[0] = __fma_rn(c, w0, acc[0]);
+            acc[1] = __fma_rn(c, w1, acc[1]);
+            acc[2] = __fma_rn(c, w2, acc[2]);
+            acc[3] = __fma_rn(c, w3, acc[3]);
+            w0 = w1; w1 = w2; w2 = w3;
+            w3 = at(pos0 - r + t + 4);
         }
-        out[i] = acc;
+#pragma unroll
+        for (int j = 0; j < kSmoothOut; ++j)
+            if (pos0 + j < len) out[base + j * step] = acc[j];
     }
 }
 

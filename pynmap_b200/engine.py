@@ -224,8 +224,9 @@ def new_accumulators(grid, sums, acc, nviews=1):
     want_maps = bool(sums & (_lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2))
     want_cube = bool(sums & _lib.SUM_CUBE)
     if nviews == 1 and want_maps and want_cube:
-        flat = torch.zeros(grid.cube_elems + grid.maps_elems, dtype=acc.dtype, device=grid.device)
-        return flat[grid.cube_elems:], flat[:grid.cube_elems]
+        pad = grid.cube_elems % 2        # keep the maps part 16-byte aligned (TMA bulk reductions)
+        flat = torch.zeros(grid.cube_elems + pad + grid.maps_elems, dtype=acc.dtype, device=grid.device)
+        return flat[grid.cube_elems + pad:], flat[:grid.cube_elems]
     maps = cube = None
     if want_maps:
         maps = torch.zeros(nviews * grid.maps_elems, dtype=acc.dtype, device=grid.device)
@@ -238,10 +239,11 @@ def reduce_span(grid, maps, cube):
     """The tensors a sum-reduction over ranks must cover once fold_maps has run: one contiguous
     view when (maps, cube) came from a joint allocation, else the two pieces."""
     folded = maps[:grid.maps_fold_elems] if maps is not None else None
-    if (maps is not None and cube is not None and maps.untyped_storage().data_ptr() == cube.untyped_storage().data_ptr()
-            and maps.storage_offset() == cube.storage_offset() + cube.numel()):
-        joint = torch.as_strided(cube, (cube.numel() + grid.maps_fold_elems,), (1,), cube.storage_offset())
-        return (joint,)
+    if maps is not None and cube is not None and maps.untyped_storage().data_ptr() == cube.untyped_storage().data_ptr():
+        gap = maps.storage_offset() - (cube.storage_offset() + cube.numel())
+        if 0 <= gap <= 1:
+            joint = torch.as_strided(cube, (cube.numel() + gap + grid.maps_fold_elems,), (1,), cube.storage_offset())
+            return (joint,)
     return tuple(t for t in (folded, cube) if t is not None)
 
 
