@@ -1,0 +1,193 @@
+"""GPU (-m gpu): the five BASELINE.json configurations at sizes the oracle finishes in seconds,
+compared with the C oracle (fixed point: bit-exact; float64 atomics: 1e-12), plus float64 particle
+arrays (what the reference's ascii reader produces) and the non-uniform-edge path of the C ABI."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import oracle_c as oc
+from oracle import oracle_np as on
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import pynmap_b200
+    import workloads
+    pynmap_b200._lib.require_device()
+    return pynmap_b200, workloads
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and np.array_equal(a, b, equal_nan=True)
+
+
+def close(a, b, tol=1e-12):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return bool(np.all(np.abs(a - b) <= tol * np.abs(b) + 1e-300))
+
+
+def test_config1_disk_256_maps(env):
+    """C1: 10^6-particle exponential disk, rotate(30, 60), 256x256 M/V/sigma maps -- full, un-chunked."""
+    pnm, wl = env
+    soa = wl.make_snapshot(1_000_000, bulge_fraction=0.0, seed=1234, device="cuda", unit_mass=False)
+    host = soa.cpu().numpy()
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="numpy")
+    snap.rotate(PA=30., inclination=60.)
+    vm = snap.velocity_moments(weight_name="mass", limXY=wl.LIM_XY, nXY=256)
+    mat = on.rotation_matrix(np.float32(30.), np.float32(60.))
+    ex = on.bin_edges(-15, 15, 256)
+    omaps, _ = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, ex, ex, None, 7)
+    Mo, Vo, So = oc.finalize_vmaps(omaps[0], None, 7)
+    assert vm.M.shape == (256, 256)
+    assert close(vm.M, Mo) and same(vm.M == 0, Mo == 0)
+    assert rel_err(vm.V, Vo, floor=1e-3) < 1e-9
+    ok = So > 1.0
+    assert rel_err(vm.S[ok], So[ok]) < 1e-8
+    # unweighted run: exact integer counts == bin indices bit-exact
+    cnt = snap.velocity_moments(limXY=wl.LIM_XY, nXY=256)
+    cmaps, _ = oc.project_bin(list(host[:6]), None, mat, 1, 1, ex, ex, None, 7)
+    assert same(cnt.M, cmaps[0, :, :, 0])
+    # fixed point: bit-exact against the oracle's quantisation
+    fx = snap.velocity_moments(weight_name="mass", limXY=wl.LIM_XY, nXY=256, accumulate="fixed")
+    from pynmap_b200 import engine
+    scales = snap._fixed_scales(engine.AccMode("fixed"), snap.mass)
+    fmaps, _ = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, ex, ex, None, 7, oc.ACC_FIXED, scales)
+    Mf, Vf, Sf = oc.finalize_vmaps(fmaps[0], None, 7, oc.ACC_FIXED, scales)
+    assert same(fx.M, Mf) and same(fx.V, Vf) and same(fx.S, Sf)
+
+
+def test_config3_512_maps_and_shard_sum(env):
+    """C3 at reduced N: 512x512 maps; two particle shards binned separately and summed give the
+    single-pass bits in fixed point (what the NCCL reduce does across GPUs)."""
+    pnm, wl = env
+    from pynmap_b200 import engine
+    from pynmap_b200.sharded import shard_bounds
+    n = 2_000_003
+    soa = wl.make_snapshot(n, seed=1236, device="cuda", unit_mass=False)
+    host = soa.cpu().numpy()
+    mat = on.rotation_matrix(np.float32(30.), np.float32(60.))
+    grid = engine.get_grid(wl.LIM_XY, 512, 512)
+    fx = engine.AccMode("fixed")
+    scales = engine.fixed_scales(n, 2.0, 2.0 * float(np.abs(host[3:6]).max()))
+    rows = [soa[k] for k in range(6)]
+    whole, _ = engine.new_accumulators(grid, 7, fx)
+    engine.project_bin(grid, rows, soa[6], mat, 1, 1, 7, fx, scales, whole, None)
+    parts = []
+    for r in range(2):
+        lo, hi = shard_bounds(n, r, 2)
+        m, _ = engine.new_accumulators(grid, 7, fx)
+        engine.project_bin(grid, [t[lo:hi] for t in rows], soa[6][lo:hi], mat, 1, 1, 7, fx, scales, m, None)
+        parts.append(engine.fold_maps(grid, m, fx).clone())
+    assert torch.equal(parts[0] + parts[1], engine.fold_maps(grid, whole, fx))
+    omaps, _ = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, grid.edges_x, grid.edges_y, None, 7, oc.ACC_FIXED, scales)
+    got = engine.fold_maps(grid, whole, fx).cpu().numpy().reshape(512, 512, 4)
+    assert np.array_equal(got[..., [2, 0, 1]], omaps[0][..., :3])
+
+
+def test_config4_views_batched(env):
+    """C4 at reduced N: 64 viewing angles (8 inclinations x 8 PAs) from one read == 64 single views."""
+    pnm, wl = env
+    n = 300_000
+    soa = wl.make_snapshot(n, seed=1237, device="cuda")
+    host = soa.cpu().numpy()
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="numpy")
+    incs = np.repeat(np.linspace(0, 87.5, 8), 8)
+    pas = np.tile(np.linspace(0, 157.5, 8), 8)
+    views = snap.project_views(pas, incs, weight_name="mass", limXY=wl.LIM_XY, nXY=64)
+    assert len(views) == 64
+    ex = on.bin_edges(-15, 15, 64)
+    for k in (0, 9, 27, 63):
+        mat = on.rotation_matrix(np.float32(pas[k]), np.float32(incs[k]))
+        omaps, _ = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, ex, ex, None, 7)
+        Mo, Vo, So = oc.finalize_vmaps(omaps[0], None, 7)
+        assert same(views[k].M, Mo)                       # unit masses: exact counts per view
+        assert rel_err(views[k].V, Vo, floor=1e-3) < 1e-9
+        assert float(views[k].PAs[0]) == float(np.float32(pas[k]))
+
+
+def test_config5_flux_weights_big_cube(env):
+    """C5 at reduced N: flux-weighted create_map (256x256) and a 256x256x512 LOSVD cube, weights
+    spanning the SSP M/L range (0.07 .. 8.6)."""
+    pnm, wl = env
+    n = 1_500_000
+    soa = wl.make_snapshot(n, seed=1238, device="cuda")
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    ml = 0.067 + (8.6 - 0.067) * torch.rand(n, generator=gen, device="cuda")
+    flux = (soa[6] / ml).float()
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], flux=flux, output="numpy")
+    snap.rotate(PA=30., inclination=60.)
+    host, fh = soa.cpu().numpy(), flux.cpu().numpy()
+    mat = on.rotation_matrix(np.float32(30.), np.float32(60.))
+    rx, ry, _ = oc.rotate(mat, host[0], host[1], host[2])
+    fm = snap.create_map(weight_name="lum", limXY=wl.LIM_XY, nXY=256)           # data = mass, weights = flux
+    _, _, W, D, DW = on.points_2map(rx, ry, host[6], weights=fh, limXY=wl.LIM_XY, nXY=256)
+    assert close(fm.W, W) and close(fm.DW, DW) and rel_err(fm.D, D, floor=1e-6) < 1e-9
+    lv = snap.create_losvds(weight_name="lum", limXY=wl.LIM_XY, nXY=256, limV=wl.LIM_V, nV=512)
+    ex, ev = on.bin_edges(-15, 15, 256), on.bin_edges(-500, 500, 512)
+    _, ocube = oc.project_bin(list(host[:6]), fh, mat, 1, 1, ex, ex, ev, 8)
+    assert lv.losvd.shape == (256, 256, 512)
+    assert close(lv.losvd, ocube[0]) and same(lv.losvd == 0, ocube[0] == 0)
+    sm = lv.convolve_spatial(0.5, 0.8)
+    assert sm.losvd.shape == lv.losvd.shape and abs(sm.losvd.sum() / lv.losvd.sum() - 1) < 1e-2
+
+
+def test_float64_particles_fused(env):
+    """The reference's reader yields float64 positions / velocities / masses (np.loadtxt): the whole
+    fused path in float64 arithmetic, 56 B per particle."""
+    pnm, wl = env
+    from pynmap_b200 import engine
+    n = 400_001
+    soa32 = wl.make_snapshot(n, seed=1239, device="cuda", unit_mass=False)
+    jitter = torch.rand((7, n), generator=torch.Generator(device="cuda").manual_seed(1), device="cuda", dtype=torch.float64)
+    soa = soa32.double() * (1.0 + 1e-9 * jitter)          # values that are NOT representable in float32
+    host = soa.cpu().numpy()
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="numpy")
+    snap.rotate(PA=12.5, inclination=77.)
+    vm, lv = snap.project(weight_name="mass", limXY=wl.LIM_XY, nXY=96, limV=wl.LIM_V, nV=64, accumulate="fixed")
+    mat = on.rotation_matrix(np.float32(12.5), np.float32(77.))
+    ex, ev = on.bin_edges(-15, 15, 96), on.bin_edges(-500, 500, 64)
+    scales = snap._fixed_scales(engine.AccMode("fixed"), snap.mass)
+    fmaps, fcube = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, ex, ex, ev, 31, oc.ACC_FIXED, scales)
+    Mf, Vf, Sf = oc.finalize_vmaps(fmaps[0], fcube[0], 31, oc.ACC_FIXED, scales)
+    assert same(vm.M, Mf) and same(vm.V, Vf) and same(vm.S, Sf)
+    assert same(lv.losvd, fcube[0].astype(np.float64) * (1.0 / scales[0]))
+    assert same(snap.pos, np.stack(oc.rotate(mat, host[0], host[1], host[2]), 1))
+
+
+def test_non_uniform_edges_through_the_abi(env):
+    """pnm_grid_create accepts any increasing edges; far from an affine grid the guard band disables
+    the uniform guess and every particle is decided by the exact table search."""
+    pnm, wl = env
+    from pynmap_b200 import _lib, engine
+    rng = np.random.default_rng(11)
+    ex = np.sort(rng.uniform(-3, 3, 41)); ey = np.concatenate([[-2.0], np.cumsum(rng.uniform(0.01, 0.3, 30)) - 2.0])
+    ev = np.array([-100., -50., -49., 0., 0.5, 200.])
+    n = 200_000
+    pts = [rng.normal(0, 1.5, n).astype(np.float32), rng.normal(0, 1.5, n).astype(np.float32), rng.normal(0, 80, n).astype(np.float32)]
+    pts[0][:41] = ex.astype(np.float32)                   # points on the (rounded) edges
+    w = rng.uniform(0.5, 2, n).astype(np.float32)
+    h = ctypes.c_void_p()
+    _lib.call("pnm_grid_create", 40, _lib.doubles(ex), 30, _lib.doubles(ey), 5, _lib.doubles(ev), ctypes.byref(h))
+    lib = _lib.load()
+    R = lib.pnm_grid_map_replicas(h)
+    maps = torch.zeros(lib.pnm_maps_acc_elems(h), dtype=torch.int64, device="cuda")
+    cube = torch.zeros(lib.pnm_cube_acc_elems(h), dtype=torch.int64, device="cuda")
+    dev = [torch.from_numpy(a).cuda() for a in pts] + [torch.from_numpy(w).cuda()]
+    scales = engine.fixed_scales(n, 2.0, 500.0)
+    P = engine.ptr
+    _lib.call("pnm_bin_points", h, n, _lib.F32, P(dev[0]), P(dev[1]), P(dev[2]), P(dev[3]), None, 0, 15, _lib.ACC_FIXED,
+              _lib.doubles(scales), P(maps), P(cube), engine.stream_ptr())
+    _lib.call("pnm_fold_maps", h, P(maps), _lib.ACC_FIXED, engine.stream_ptr())
+    out = torch.empty((40, 30, 5), dtype=torch.float64, device="cuda")
+    _lib.call("pnm_finalize_cube", h, P(cube), _lib.ACC_FIXED, float(scales[0]), P(out), engine.stream_ptr())
+    omaps, ocube = oc.project_bin(pts, w, None, 1, 1, ex, ey, ev, 15, oc.ACC_FIXED, scales, fused=False)
+    got = maps[:40 * 30 * 4].cpu().numpy().reshape(30, 40, 4)
+    assert R >= 1 and np.array_equal(got[..., [2, 0, 1]], omaps[0][..., :3])
+    assert np.array_equal(out.cpu().numpy(), ocube[0].astype(np.float64) * (1.0 / scales[0]))
+    lib.pnm_grid_destroy(h)
