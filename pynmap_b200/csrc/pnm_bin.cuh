@@ -132,42 +132,44 @@ __device__ __forceinline__ void red_add(long long* p, long long v) {
 }
 
 // ---- TMA staging of (S1, S2) pairs ---------------------------------------------------------------
-// Shared-memory layout per CTA: kTmaStages x kTmaSlots x blockDim.x records of 16 bytes (conflict
-// free: consecutive threads, consecutive records) + the matching destination offsets.  A thread
+// Shared-memory layout per CTA: kTmaStages x kTmaSlots x blockDim.x records of 32 bytes
+// (S1, S2, S0, pad; consecutive threads, consecutive records) + the matching destination offsets.  A thread
 // only ever touches its own records, so ordering needs no CTA barrier: generic-proxy writes ->
 // fence.proxy.async -> bulk reductions -> commit_group; before a stage is rewritten two tiles
 // later, wait_group.read 1 guarantees the TMA unit has read it.
 // of the (up to) 8 map updates of a tile; the rest take the LSU path.  Measured on the bench
 // workload (1e8 particles, maps + cube): 0 -> 1.78 ms, 2 -> 1.65, 4 -> 1.59, 5 -> 1.67, 6 -> 1.82
-constexpr int kTmaSlots = 4;
+constexpr int kTmaSlots = 6;      // capacity; the launcher picks how many are used (BinParams::tma_slots)
 constexpr int kTmaStages = 2;
 
 __device__ __forceinline__ void tma_fence_writes() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read_1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_reduce16(double* dst, const void* src_smem) {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 16;"
-                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)) : "memory");
+// 16 bytes = (S1, S2); 32 bytes = (S1, S2, S0, pad) when the record also carries sum w
+__device__ __forceinline__ void tma_reduce(double* dst, const void* src_smem, int bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void tma_reduce16(long long* dst, const void* src_smem) {
-    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], 16;"
-                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)) : "memory");
+__device__ __forceinline__ void tma_reduce(long long* dst, const void* src_smem, int bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.u64 [%0], [%1], %2;"
+                 :: "l"(dst), "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes) : "memory");
 }
 
 template <int ACC>
 struct TmaStage {
     using A = typename AccT<ACC>::type;
-    A* vals;        // this thread's record 0 of the current stage (record k at vals + 2*k*stride)
-    int* offs;      // destination offsets, same indexing (offs + k*stride)
+    A* vals;        // this thread's record 0 of the current stage (record k at vals + 4*k*stride)
+    int* offs;      // destination offsets (negated - 1 when the record carries S0), offs + k*stride
     int stride;     // blockDim.x
     int used, cap;  // records filled in this tile, capacity (0 disables the TMA path)
 
-    __device__ __forceinline__ bool push(int off, A s1, A s2) {
+    __device__ __forceinline__ bool push(int off, A s1, A s2, A s0, bool with0) {
         if (used >= cap) return false;
-        A* rec = vals + 2 * used * stride;
-        rec[0] = s1; rec[1] = s2;                       // one STS.128
-        offs[used * stride] = off;
+        A* rec = vals + 4 * used * stride;
+        rec[0] = s1; rec[1] = s2;                       // STS.128
+        if (with0) { rec[2] = s0; rec[3] = 0; }
+        offs[used * stride] = with0 ? -off - 1 : off;
         ++used;
         return true;
     }
@@ -176,7 +178,10 @@ struct TmaStage {
         if (cap == 0) return;
         if (used > 0) {
             tma_fence_writes();
-            for (int k = 0; k < used; ++k) tma_reduce16(maps + offs[k * stride] + kSlotS1, vals + 2 * k * stride);
+            for (int k = 0; k < used; ++k) {
+                const int o = offs[k * stride];
+                tma_reduce(maps + (o < 0 ? -o - 1 : o), vals + 4 * k * stride, o < 0 ? 32 : 16);
+            }
         }
         tma_commit();                                   // (possibly empty) group: keeps the group count in step
         used = 0;
@@ -193,9 +198,10 @@ struct MapRun {
 
     __device__ __forceinline__ void flush(A* maps, int sums, TmaStage<ACC>& st) {
         if (off < 0) return;
-        if ((sums & PNM_SUM_W) && has0) red_add(maps + off + kSlotS0, s0);
+        const bool with0 = (sums & PNM_SUM_W) && has0;
         const bool both = (sums & PNM_SUM_WD) && (sums & PNM_SUM_WD2);
-        if (!(both && st.push(off, s1, s2))) {
+        if (!(both && st.push(off, s1, s2, s0, with0))) {
+            if (with0) red_add(maps + off + kSlotS0, s0);
             if (sums & PNM_SUM_WD) red_add(maps + off + kSlotS1, s1);
             if (sums & PNM_SUM_WD2) red_add(maps + off + kSlotS2, s2);
         }
@@ -294,7 +300,7 @@ __host__ __device__ inline size_t bin_table_bytes(int nx, int ny, int nv) {
     return (((size_t)(nx + 1) + (ny + 1) + (nv + 1)) * sizeof(T) + 15) & ~(size_t)15;
 }
 __host__ __device__ inline size_t bin_stage_bytes(int threads) {
-    return (size_t)kTmaStages * kTmaSlots * threads * (16 + 4);
+    return (size_t)kTmaStages * kTmaSlots * threads * (32 + 4);
 }
 
 // ---- kernel: persistent grid-stride loop; each thread takes Pack<T>::N consecutive particles per
@@ -333,11 +339,11 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
     // TMA staging (SIMPLE + vector path only): [stage][slot][thread] records, then the offsets
     unsigned char* stage_raw = smem_raw + bin_table_bytes<T>(p.nx, p.ny, p.nv);
     A* const stage_vals = reinterpret_cast<A*>(stage_raw);
-    int* const stage_offs = reinterpret_cast<int*>(stage_raw + (size_t)kTmaStages * kTmaSlots * blockDim.x * 16);
+    int* const stage_offs = reinterpret_cast<int*>(stage_raw + (size_t)kTmaStages * kTmaSlots * blockDim.x * 32);
     TmaStage<ACC> st;
     st.stride = blockDim.x; st.used = 0;
     st.cap = (SIMPLE && VECLOAD) ? p.tma_slots : 0;
-    st.vals = stage_vals + 2 * threadIdx.x;
+    st.vals = stage_vals + 4 * threadIdx.x;
     st.offs = stage_offs + threadIdx.x;
 
     auto one = [&](int64_t idx, T x, T y, T z, T vx, T vy, T vz, T w, MapRun<ACC>& run) {
@@ -379,7 +385,7 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
             if (W) Pack<T>::load(W + i * VN, w);
             if (st.cap) {                                   // the stage used two tiles ago must have been read
                 tma_wait_read_1();
-                st.vals = stage_vals + ((size_t)parity * kTmaSlots * blockDim.x + threadIdx.x) * 2;
+                st.vals = stage_vals + ((size_t)parity * kTmaSlots * blockDim.x + threadIdx.x) * 4;
                 st.offs = stage_offs + (size_t)parity * kTmaSlots * blockDim.x + threadIdx.x;
                 parity ^= 1;
             }

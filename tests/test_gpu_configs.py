@@ -101,6 +101,9 @@ def test_config4_views_batched(env):
     pas = np.tile(np.linspace(0, 157.5, 8), 8)
     views = snap.project_views(pas, incs, weight_name="mass", limXY=wl.LIM_XY, nXY=64)
     assert len(views) == 64
+    # the same views binned 16 per read of the particles (pnm_project_bin with nviews = 16)
+    batched = snap.project_views(pas[:32], incs[:32], weight_name="mass", limXY=wl.LIM_XY, nXY=64, views_per_launch=16)
+    assert all(same(batched[k].M, views[k].M) and rel_err(batched[k].V, views[k].V, floor=1e-3) < 1e-9 for k in range(32))
     ex = on.bin_edges(-15, 15, 64)
     for k in (0, 9, 27, 63):
         mat = on.rotation_matrix(np.float32(pas[k]), np.float32(incs[k]))
