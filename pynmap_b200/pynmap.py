@@ -435,8 +435,15 @@ class snapshot(object):
         grid = engine.get_grid(limXY, n2[0], n2[1], limV, int(nV))
         w = self._weights_on_device(weights)
         sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2 | _lib.SUM_CUBE | _lib.W_FROM_CUBE
-        n_total, reduce_max = (reducer.n_total(self.npart), reducer.reduce_max) if reducer else (None, None)
-        scales = self._fixed_scales(acc, w, n_total, reduce_max)
+        scales = None
+        if acc.code == _lib.ACC_FIXED:
+            # sharded fixed-point runs agree on the global particle count and bounds (cached: the
+            # two tiny all-reduces end in a host read and would serialise every step)
+            key = ("fixed", id(reducer), None if w is None else w.data_ptr(), id(self._base[1]))
+            if key not in self._absmax:
+                n_total, reduce_max = (reducer.n_total(self.npart), reducer.reduce_max) if reducer else (None, None)
+                self._absmax[key] = self._fixed_scales(acc, w, n_total, reduce_max)
+            scales = self._absmax[key]
         maps, cube = self._run_fused(grid, w, sums, acc, scales)
         if reducer is not None:
             engine.fold_maps(grid, maps, acc)
