@@ -194,3 +194,36 @@ def test_non_uniform_edges_through_the_abi(env):
     assert R >= 1 and np.array_equal(got[..., [2, 0, 1]], omaps[0][..., :3])
     assert np.array_equal(out.cpu().numpy(), ocube[0].astype(np.float64) * (1.0 / scales[0]))
     lib.pnm_grid_destroy(h)
+
+
+def test_host_path_single_and_sharded_flavours(env):
+    """hostpath.project_host: the single-call C-ABI path (pnm_project_host) and the sharded path
+    (pnm_accumulate_host + reducer + finalise) give the same answer as the device-resident API,
+    with smoothing, pinned torch buffers or plain numpy arrays as inputs."""
+    pnm, wl = env
+    from pynmap_b200 import hostpath
+    n = 5_000_011                                        # two staging chunks, ragged
+    soa = wl.make_snapshot(n, seed=1240, device="cuda", unit_mass=False)
+    host = soa.cpu().numpy()
+    pinned = torch.empty((7, n), dtype=torch.float32, pin_memory=True)
+    pinned.copy_(soa)
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="numpy")
+    snap.rotate(PA=30., inclination=60.)
+    vm, lv = snap.project(weight_name="mass", limXY=wl.LIM_XY, nXY=64, limV=wl.LIM_V, nV=32)
+    sm = lv.convolve_spatial(1.0, 1.0)
+    single = hostpath.project_host([host[k] for k in range(7)], 30., 60., wl.LIM_XY, 64, wl.LIM_V, 32, smooth_fwhm=(1.0, 1.0))
+    calls = []
+    def fake_reducer(*tensors):                          # world size 1: nothing to add, rank 0 holds the total
+        calls.append([t.numel() for t in tensors])
+        return True
+    sharded = hostpath.project_host([pinned[k] for k in range(7)], 30., 60., wl.LIM_XY, 64, wl.LIM_V, 32,
+                                    smooth_fwhm=(1.0, 1.0), reducer=fake_reducer)
+    assert calls == [[64 * 64 * 32 + 64 * 64 * 4]]       # one contiguous span: cube + folded maps
+    for res in (single, sharded):
+        assert close(res["M"], vm.M) and rel_err(res["V"], vm.V, floor=1e-3) < 1e-9
+        assert np.allclose(res["cube"], sm.losvd, rtol=1e-10, atol=1e-12 * sm.losvd.max())
+    unsmoothed = hostpath.project_host([host[k] for k in range(7)], 30., 60., wl.LIM_XY, 64, wl.LIM_V, 32)
+    assert close(unsmoothed["cube"], lv.losvd)
+    with pytest.raises(ValueError):
+        hostpath.project_host([host[k] for k in range(7)], 30., 60., wl.LIM_XY, 64, wl.LIM_V, 32, accumulate="fixed")
+    pnm._lib.call("pnm_host_release")
