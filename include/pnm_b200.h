@@ -160,6 +160,13 @@ int pnm_smooth_cube(const double* cube_in, double* cube_out, double* work,
                     const double* taps0_host, int32_t ntaps0,
                     const double* taps1_host, int32_t ntaps1, void* stream);
 
+/* ---- f3: integer-factor spatial rebin of every velocity slice (losvd.py:69-92, misc_io.py:383-394)
+ * cube_out[i][j][k] = sum (mean != 0: mean) of the factor_x * factor_y block of cube_in, summed
+ * first along Y then along X like rebin_2darray.  cube_in (nx, ny, nv) must have nx, ny divisible
+ * by the factors (the reference's reshape raises otherwise; the host layer checks).            */
+int pnm_rebin_cube(const double* cube_in, double* cube_out, int32_t nx, int32_t ny, int32_t nv,
+                   int32_t factor_x, int32_t factor_y, int mean, void* stream);
+
 /* ---- f1: per-spaxel moments of the cube (losvd.py:41-51, misc_functions.py:70-90) ----------
  * mom0 = sum_k c, mom1 = sum_k v c / mom0, mom2 = sqrt(sum_k v^2 c / mom0 - mom1^2); (nx, ny).
  * An all-zero spaxel gives (0, 0, empty_m2), empty_m2 = min(diff(binv)) / 3 from the host.     */

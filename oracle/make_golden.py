@@ -136,6 +136,10 @@ def main():
         out.update({"smooth_eq": c1.losvd, "smooth_neq": c2.losvd, "smooth_twice": c3.losvd})
         quiet(Lw.vmoments)
         out.update({"mom0": Lw.mom0, "mom1": Lw.mom1, "mom2": Lw.mom2})
+        # integer-factor rebin (losvd.py:69-92): sum and mean, coordinates through the same function
+        rs, rm = quiet(Lw.rebin_spatial, 4, 2), quiet(Lw.rebin_spatial, 2, 4, "mean")
+        out.update({"rebin_sum": rs.losvd, "rebin_sum_binx": rs.binx, "rebin_sum_biny": rs.biny,
+                    "rebin_mean": rm.losvd, "rebin_mean_binx": rm.binx, "rebin_mean_biny": rm.biny})
         save("grid_%s" % np.dtype(dt).name, **out)
 
     # ---- snapshot level: ascii file -> rotate -> velocity_moments / create_map / create_losvds

@@ -114,6 +114,17 @@ def smooth_cube(cube, ker2d):
     return out
 
 
+def rebin_cube(cube, factorx, factory, mean=False):
+    cube = _c(cube, np.float64)
+    nx, ny, nv = cube.shape
+    out = np.empty((nx // factorx, ny // factory, nv), dtype=np.float64)
+    L = lib()
+    L.pnmo_rebin_cube.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]
+    L.pnmo_rebin_cube.restype = None
+    L.pnmo_rebin_cube(_p(cube), _p(out), nx, ny, nv, int(factorx), int(factory), 1 if mean else 0)
+    return out
+
+
 def cube_moments(cube, binv):
     cube = _c(cube, np.float64)
     binv = _c(binv, np.float64)

@@ -353,6 +353,24 @@ def convolve_spatial(cube, stepx, stepy, fwhmx, fwhmy, cur_fwhmx=0.0, cur_fwhmy=
     return out, rx, ry
 
 
+# --------------------------------------------------------------------------- rebin (f3)
+def rebin_spatial(cube, binx, biny, factorx=1, factory=1, function="sum"):
+    """losvd.py:69-92 with misc_io.py:370-394: per velocity slice
+    a.reshape(n0, fx, n1, fy).sum(-1).sum(1) (or .mean(-1).mean(1)); binx / biny through the same
+    function (so 'sum' SUMS the centres).  Raises ValueError like the reference's reshape when the
+    shape is not a multiple of the factors."""
+    nx, ny, nv = cube.shape
+    n0, n1 = nx // factorx, ny // factory
+    red = (lambda a, ax: a.mean(ax)) if function == "mean" else (lambda a, ax: a.sum(ax))
+    bx = red(np.asarray(binx).reshape((n0, nx // n0)), -1)
+    by = red(np.asarray(biny).reshape((n1, ny // n1)), -1)
+    out = np.zeros((n0, n1, nv))
+    for k in range(nv):
+        a = cube[:, :, k].reshape((n0, nx // n0, n1, ny // n1))
+        out[:, :, k] = red(red(a, -1), 1)
+    return bx, by, out
+
+
 # --------------------------------------------------------------------------- LOSVD moments (f1)
 def moment012(x, data):
     """misc_functions.py:70-90."""

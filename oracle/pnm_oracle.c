@@ -200,6 +200,24 @@ void pnmo_smooth_cube(const double* in, double* out, int nx, int ny, int nv, con
             }
 }
 
+/* ---- losvd.py:69-92 + misc_io.py:383-394: reshape(n0, fx, n1, fy).sum(-1).sum(1) per slice ---- */
+void pnmo_rebin_cube(const double* in, double* out, int nx, int ny, int nv, int fx, int fy, int mean) {
+    const int n0 = nx / fx, n1 = ny / fy;
+    (void)nx;
+    for (int i = 0; i < n0; ++i)
+        for (int j = 0; j < n1; ++j)
+            for (int k = 0; k < nv; ++k) {
+                double acc = 0.0;
+                for (int a = 0; a < fx; ++a) {
+                    double s = 0.0;
+                    for (int b = 0; b < fy; ++b) s += in[((int64_t)(i * fx + a) * ny + (j * fy + b)) * nv + k];
+                    if (mean) s /= (double)fy;
+                    acc += s;
+                }
+                out[((int64_t)i * n1 + j) * nv + k] = mean ? acc / (double)fx : acc;
+            }
+}
+
 /* ---- losvd.py:41-51 + misc_functions.py:70-90 ---- */
 void pnmo_cube_moments(const double* cube, int nx, int ny, int nv, const double* binv, double* m0, double* m1, double* m2) {
     double mind = INFINITY;

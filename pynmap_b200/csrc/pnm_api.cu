@@ -423,6 +423,19 @@ int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv, con
     return PNM_OK;
 }
 
+int pnm_rebin_cube(const double* cube_in, double* cube_out, int32_t nx, int32_t ny, int32_t nv,
+                   int32_t factor_x, int32_t factor_y, int mean, void* stream) {
+    if (!cube_in || !cube_out || cube_in == cube_out) return fail(PNM_EINVAL, "pnm_rebin_cube: bad buffers");
+    if (nx < 1 || ny < 1 || nv < 1 || factor_x < 1 || factor_y < 1 || factor_x > nx || factor_y > ny)
+        return fail(PNM_EINVAL, "pnm_rebin_cube: bad shape / factors");
+    const int n0 = nx / factor_x, n1 = ny / factor_y;        // trailing rows / columns are dropped by the caller's reshape rule
+    const int64_t total = (int64_t)n0 * n1 * nv;
+    pnm::k_rebin_cube<<<grid_for(total, 256, 8), 256, 0, as_stream(stream)>>>(cube_in, cube_out, ny, nv, n0, n1,
+                                                                             factor_x, factor_y, mean ? 1 : 0);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
 int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream) {
     if (!out_dev || n < 0 || (n > 0 && !a)) return fail(PNM_EINVAL, "pnm_absmax: bad argument");
     PNM_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), as_stream(stream)));

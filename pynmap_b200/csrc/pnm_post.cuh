@@ -189,6 +189,29 @@ __global__ void __launch_bounds__(256) k_smooth_axis(const double* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------- f3: integer-factor spatial rebin
+// losvd.py:69-92 via misc_io.py:383-394 (rebin_2darray): a.reshape(n0, fx, n1, fy).sum(-1).sum(1)
+// per velocity slice, i.e. first the fy neighbours along Y, then the fx partial sums along X
+// ('mean' divides by fy, then by fx, like the two chained .mean calls).
+__global__ void __launch_bounds__(256) k_rebin_cube(const double* __restrict__ in, double* __restrict__ out,
+                                                    int ny, int nv, int n0, int n1, int fx, int fy, int mean) {
+    const int total = n0 * n1 * nv;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int k = i % nv, rest = i / nv;
+        const int j = rest % n1, io = rest / n1;
+        double acc = 0.0;
+        for (int a = 0; a < fx; ++a) {
+            const double* row = in + ((int64_t)(io * fx + a) * ny + (int64_t)j * fy) * nv + k;
+            double s = 0.0;
+            for (int b = 0; b < fy; ++b) s = __dadd_rn(s, row[(int64_t)b * nv]);
+            if (mean) s = __ddiv_rn(s, (double)fy);
+            acc = __dadd_rn(acc, s);
+        }
+        out[i] = mean ? __ddiv_rn(acc, (double)fx) : acc;
+    }
+}
+
 // ---------------------------------------------------------------- f1: per-spaxel LOSVD moments
 // losvd.py:41-51 + misc_functions.py:70-90: one warp per spaxel, shuffle reduction over iv.
 // An all-zero LOSVD gives (0, 0, min(diff(binv))/3) (misc_functions.py:81-84) = empty_m2.

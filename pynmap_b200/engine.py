@@ -370,6 +370,16 @@ def smooth_cube(cube, taps_axis0, taps_axis1):
     return out
 
 
+def rebin_cube(cube, factorx, factory, mean=False):
+    """pnm_rebin_cube on a float64 (nX, nY, nV) device tensor -> (nX//fx, nY//fy, nV)."""
+    cube = cube.contiguous()
+    nx, ny, nv = cube.shape
+    out = torch.empty((nx // factorx, ny // factory, nv), dtype=torch.float64, device=cube.device)
+    _lib.call("pnm_rebin_cube", ptr(cube), ptr(out), nx, ny, nv, int(factorx), int(factory), 1 if mean else 0,
+              stream_ptr())
+    return out
+
+
 def cube_moments(cube, binv):
     cube = cube.contiguous()
     nx, ny, nv = cube.shape

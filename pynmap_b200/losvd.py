@@ -61,6 +61,36 @@ class LOSVD(object):
         m0, m1, m2 = engine.cube_moments(cube, _np(self.binv))
         self.mom0, self.mom1, self.mom2 = (engine.to_output(m, want_torch) for m in (m0, m1, m2))
 
+    # ------------------------------------------------------------------ f3: spatial rebin
+    def rebin_spatial(self, factorx=1, factory=1, function='sum'):
+        """Rebin by integer factors in X and Y (pynmap/losvd.py:69-92 with misc_io.rebin_1darray /
+        rebin_2darray, misc_io.py:370-394).  Quirk kept: ``binx`` / ``biny`` go through the same
+        ``function``, so with the default 'sum' the new coordinates are SUMS of the old centres."""
+        nx, ny = int(self.losvd.shape[0]), int(self.losvd.shape[1])
+        newshape = (nx // factorx, ny // factory)
+        print("Newshape will be {}".format(newshape))
+        if function not in ('sum', 'mean'):
+            print("WARNING: doing the sum as input function {}  not recognised".format(function))
+        mean = function == 'mean'
+        if newshape[0] * factorx != nx or newshape[1] * factory != ny:
+            # a.reshape(sh) of the reference fails for sizes that are not multiples of the factors
+            raise ValueError("cannot reshape array of size {} into shape {}".format(
+                nx * ny, (newshape[0], factorx, newshape[1], factory)))
+
+        def rebin1d(a, n, f):
+            a = _np(a).reshape((n, f))
+            return a.mean(-1) if mean else a.sum(-1)
+
+        binx = rebin1d(self.binx, newshape[0], factorx)
+        biny = rebin1d(self.biny, newshape[1], factory)
+        cube, want_torch = self._cube_on_device(self.losvd)
+        losvd = engine.to_output(engine.rebin_cube(cube, factorx, factory, mean), want_torch)
+        err_losvd = None
+        if self._has_errors():
+            ecube, e_torch = self._cube_on_device(self.err_losvd)
+            err_losvd = engine.to_output(engine.rebin_cube(ecube, factorx, factory, mean), e_torch)
+        return LOSVD(binx, biny, self.binv, losvd, err_losvd, self.fwhmx, self.fwhmy)
+
     # ------------------------------------------------------------------ a5: smoothing
     def convolve_spatial(self, fwhmx=None, fwhmy=None):
         """Smooth every velocity slice to the target FWHM (pynmap/losvd.py:94-141).

@@ -291,6 +291,22 @@ def test_smoothing_and_vmoments(pnm, golden, dtname):
     assert np.allclose(L.mom2[wide], g["mom2"][wide], rtol=1e-9)
 
 
+@pytest.mark.parametrize("dtname", ["float32", "float64"])
+def test_rebin_spatial(pnm, golden, dtname):
+    """f3: LOSVD.rebin_spatial (losvd.py:69-92) against the reference's output."""
+    g = golden("grid_" + dtname)
+    L = pnm.LOSVD(g["binx"], g["biny"], g["binv"], g["cube_w"], fwhmx=0.3, fwhmy=0.4)
+    rs, rm = L.rebin_spatial(4, 2), L.rebin_spatial(2, 4, "mean")
+    assert rs.losvd.shape == (10, 16, 20) and (rs.fwhmx, rs.fwhmy) == (0.3, 0.4)
+    assert np.allclose(rs.losvd, g["rebin_sum"], rtol=1e-14, atol=0) and same(rs.binx, g["rebin_sum_binx"])
+    assert np.allclose(rm.losvd, g["rebin_mean"], rtol=1e-14, atol=0) and same(rm.biny, g["rebin_mean_biny"])
+    assert same(rs.biny, g["rebin_sum_biny"]) and same(rm.binx, g["rebin_mean_binx"])
+    with pytest.raises(ValueError):
+        L.rebin_spatial(3, 2)
+    Lt = pnm.LOSVD(g["binx"], g["biny"], g["binv"], torch.from_numpy(g["cube_w"]).cuda())
+    assert Lt.rebin_spatial(4, 2).losvd.is_cuda
+
+
 # ------------------------------------------------------------------------------- host-buffer ABI
 def test_project_host_matches_device_path(pnm):
     import ctypes

@@ -123,6 +123,19 @@ def test_smoothing_and_moments(golden, dtname):
     assert np.allclose([v[0] for v in r], g["mom0"][:3, :3].ravel())
 
 
+@pytest.mark.parametrize("dtname", ["float32", "float64"])
+def test_rebin_spatial(golden, dtname):
+    """f3: losvd.py:69-92 -- sum and mean, coordinates rebinned through the same function."""
+    g = golden("grid_" + dtname)
+    cube = g["cube_w"]
+    for key, (fx, fy, fn) in {"rebin_sum": (4, 2, "sum"), "rebin_mean": (2, 4, "mean")}.items():
+        bx, by, out = on.rebin_spatial(cube, g["binx"], g["biny"], fx, fy, fn)
+        assert same(out, g[key]) and same(bx, g[key + "_binx"]) and same(by, g[key + "_biny"])
+        assert np.allclose(oc.rebin_cube(cube, fx, fy, fn == "mean"), g[key], rtol=1e-14, atol=0)
+    with pytest.raises(ValueError):
+        on.rebin_spatial(cube, g["binx"], g["biny"], 3, 2)
+
+
 def test_snapshot_level(golden):
     """pynmap.py:246-455 through the oracle: float32 angles, rotate, maps, cube, compounded rotation."""
     g = golden("snapshot")
