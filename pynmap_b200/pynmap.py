@@ -423,11 +423,17 @@ class snapshot(object):
 
     # ------------------------------------------------------------------ additions (single read)
     def project(self, weights=None, weight_name=None, limXY=default_limXY, nXY=default_npoint,
-                limV=default_limV, nV=default_nVpoint, accumulate="f64", reducer=None):
+                limV=default_limV, nV=default_nVpoint, accumulate="f64", reducer=None, post_stream=None):
         """velocity_moments + create_losvds from ONE pass over the particles: returns
         (SnapMap, LOSVD) identical to calling the two methods separately.  The map's sum of
         weights is recovered from the cube (plus an out-of-range remainder), which saves one
-        atomic per particle.  ``reducer(maps, cube)`` is the multi-GPU hook (sharded.py)."""
+        atomic per particle.  ``reducer(maps, cube)`` is the multi-GPU hook (sharded.py).
+
+        ``post_stream``: a torch.cuda.Stream on which everything AFTER the scatter kernel runs
+        (replica fold, the reduce over ranks, finalisation).  The scatter of the next call then
+        overlaps this call's collective and post-processing; the returned tensors belong to
+        ``post_stream`` -- keep working on them inside ``with torch.cuda.stream(post_stream)``
+        and synchronise it before reading them elsewhere."""
         if weight_name is not None:
             weights = self._select_weight(weight_name)
         n2 = engine.expand_nxy(nXY)
@@ -445,6 +451,18 @@ class snapshot(object):
                 self._absmax[key] = self._fixed_scales(acc, w, n_total, reduce_max)
             scales = self._absmax[key]
         maps, cube = self._run_fused(grid, w, sums, acc, scales)
+        if post_stream is None:
+            return self._project_post(grid, maps, cube, sums, acc, scales, reducer)
+        scattered = torch.cuda.Event()
+        scattered.record()                                   # on the caller's (scatter) stream
+        post_stream.wait_event(scattered)
+        for t in (maps, cube):                               # same storage; keep it alive for the other stream
+            t.record_stream(post_stream)
+        with torch.cuda.stream(post_stream):
+            return self._project_post(grid, maps, cube, sums, acc, scales, reducer)
+
+    def _project_post(self, grid, maps, cube, sums, acc, scales, reducer):
+        """Everything after the scatter of project(): fold + reduce over ranks, finalisation."""
         if reducer is not None:
             engine.fold_maps(grid, maps, acc)
             keep = reducer(*engine.reduce_span(grid, maps, cube))
