@@ -211,7 +211,8 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # the reduce must not queue behind the scatter
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 
     import pynmap_b200 as pnm
     import workloads
@@ -227,9 +228,16 @@ def run_b200(args):
 
     # post-processing stream: replica fold, NCCL reduce, finalisation and smoothing of step k run
     # next to the scatter kernel of step k+1 (all K steps are complete before the timer stops)
-    post = None if args.no_pipeline else torch.cuda.Stream()
+    post = None if args.no_pipeline else torch.cuda.Stream(priority=-1)
+
+    counter = [0]
 
     def step():
+        if reducer is not None:
+            # round-robin owner: step k's grids are reduced to, finalised and smoothed on rank k % N,
+            # so that the post-processing load is spread over the ranks instead of piling up on rank 0
+            reducer.dst = counter[0] % world
+            counter[0] += 1
         with contextlib.redirect_stdout(sink):
             vmap, losvd = snap.project(weight_name="mass", limXY=workloads.LIM_XY, nXY=NXY, limV=workloads.LIM_V,
                                        nV=NV, accumulate=args.accumulate, reducer=reducer, post_stream=post)
@@ -324,7 +332,7 @@ def run_b200(args):
             "dtype": "f32 particles, f64 accumulators" if args.accumulate == "f64" else "f32 particles, int64 fixed-point accumulators",
             "data": "synthetic",
             "config": {"workload": workload_name(n_gpus, n_local), "particles_per_gpu": n_local, "nXY": NXY, "nV": NV,
-                       "accumulate": args.accumulate, "parallelism": "particle shards x%d + NCCL reduce of partial grids" % n_gpus
+                       "accumulate": args.accumulate, "parallelism": "particle shards x%d + NCCL reduce of partial grids (owner rank = step %% N)" % n_gpus
                        if n_gpus > 1 else "1 GPU",
                        "l2": "inputs (2.8 GB per GPU) are 22x larger than L2, no flush needed",
                        "streams": "scatter on the main stream; fold / reduce / finalise / smooth on a post-processing "
