@@ -343,7 +343,10 @@ def run_b200(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "cpu_baseline": base,
             "e2e": e2e,
-            "gpu_launches": 5 * args.steps,     # k_project_bin, k_finalize_vmaps, k_cube_out, k_smooth_axis<0>, <1> per step
+            # our kernels launched by rank 0 inside the timed region: k_project_bin (+ k_fold_maps when
+            # sharded) every step; k_finalize_vmaps, k_cube_out, k_smooth_axis<0>, <1> on the steps it owns
+            "gpu_launches": (5 * args.steps if n_gpus == 1 else
+                             2 * args.steps + 4 * len([k for k in range(args.steps) if (k + max(3, args.warmup)) % n_gpus == 0])),
             "clocks": clocks,
         }
         print(json.dumps(line))
