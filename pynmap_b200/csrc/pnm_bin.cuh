@@ -93,16 +93,18 @@ __device__ __noinline__ int exact_bin(T x, const T* thr, int n) {
 __device__ __forceinline__ float floor_t(float v) { return floorf(v); }
 __device__ __forceinline__ double floor_t(double v) { return floor(v); }
 
-// uniform guess.  Inside the grid (give or take half a bin) `sure` is cleared when x is within eps
-// (in bins) of an edge; further out the particle is certainly dropped (-1), and so is NaN.
+// uniform guess: floor((x - x0) * inv).  `sure` is cleared when the fractional part is within eps
+// of an integer (x within eps bins of an edge, first and last included), for NaN (every comparison
+// fails) and for |g| >= 2^23 (2^52), where the fraction is 0; the exact table search then decides.
+// Out-of-range guesses (negative, >= n; the conversion saturates) are dropped by the caller's
+// unsigned range check.  7 instructions per axis.
 template <typename T>
 __device__ __forceinline__ int guess_bin(T x, const Axis<T>& a, bool& sure) {
     const T g = (x - a.x0) * a.inv;
     const T f = floor_t(g);
     const T r = g - f;
-    const bool inside = (g >= (T)-0.5) && (g <= a.n_plus_half);      // false for NaN
-    sure = sure && (!inside || ((r > a.eps) && (r < a.one_m_eps)));
-    return inside ? (int)f : -1;                                      // range checked by the caller
+    sure = sure && (r > a.eps) && (r < a.one_m_eps);
+    return (int)f;
 }
 
 // ---- accumulator arithmetic --------------------------------------------------------------------
