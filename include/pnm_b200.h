@@ -167,6 +167,24 @@ int pnm_smooth_cube(const double* cube_in, double* cube_out, double* work,
 int pnm_rebin_cube(const double* cube_in, double* cube_out, int32_t nx, int32_t ny, int32_t nv,
                    int32_t factor_x, int32_t factor_y, int mean, void* stream);
 
+/* ---- f2: SSP mass-to-light weights (misc_functions.py:195-202) ------------------------------
+ * out[i] = scipy.interpolate.griddata(nodes, values, (qx[i], qy[i]), method='cubic'), i.e. the
+ * Clough-Tocher C1 cubic on the Delaunay triangulation of the table, NaN outside the convex hull,
+ * replaced by the value of the nearest node when fill_nearest != 0.  The triangulation, scipy's
+ * gradient estimate and the per-triangle Bezier ordinates are table-only work done once on the
+ * host (pynmap_b200/ssp.py); all table pointers are DEVICE pointers:
+ *   tri_xform [ntri][6]   T00 T01 T10 T11 r0 r1   (b01 = T (q - r), b2 = 1 - b0 - b1)
+ *   tri_coef  [ntri][19]  c3000 c2100 c2010 c2001 c1200 c1101 c1020 c1011 c1002 c0300 c0210 c0201
+ *                         c0120 c0111 c0102 c0030 c0021 c0012 c0003
+ *   cell_start [ncell*ncell + 1], cell_tris: CSR lists of candidate triangles per cell of a uniform
+ *   grid over the table's bounding box (cell = (floor((qx-lo0)*inv0), floor((qy-lo1)*inv1)))
+ *   nodes [nnode][3] x y value.   qx, qy: float32 or float64 (dtype); out: float64.                */
+int pnm_ct_interp(const void* qx, const void* qy, int64_t n, int dtype,
+                  const double* tri_xform, const double* tri_coef, int32_t ntri,
+                  const int32_t* cell_start, const int32_t* cell_tris, int32_t ncell,
+                  double lo0, double lo1, double inv0, double inv1,
+                  const double* nodes, int32_t nnode, int fill_nearest, double* out, void* stream);
+
 /* ---- f1: per-spaxel moments of the cube (losvd.py:41-51, misc_functions.py:70-90) ----------
  * mom0 = sum_k c, mom1 = sum_k v c / mom0, mom2 = sqrt(sum_k v^2 c / mom0 - mom1^2); (nx, ny).
  * An all-zero spaxel gives (0, 0, empty_m2), empty_m2 = min(diff(binv)) / 3 from the host.     */

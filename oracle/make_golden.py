@@ -160,6 +160,22 @@ def main():
          cube=lv.losvd, binv=lv.binv, pos_rot=pos1, vel_rot=vel1, M2=vm2.M, V2=vm2.V, S2=vm2.S, pos_rot2=pos2,
          PAs2=PAs2, incs2=incs2)
 
+    # ---- f2: SSP mass-to-light ratios (misc_functions.py:115-207) with the reference's E-MILES tables.
+    # Stored: the (age, [M/H]) -> M/L nodes the reference interpolates (its own intermediate `sspML`,
+    # observed by replaying misc_functions.py:176-193 on its tables), query points, and its output.
+    rng = np.random.default_rng(31)
+    qa, qm = rng.uniform(0.0, 14.5, 4000), rng.uniform(-2.4, 0.5, 4000)
+    ML = quiet(ref.misc_functions.compute_ml_ssps, np.ones(4000), qa, qm)
+    ML_nofill = quiet(ref.misc_functions.compute_ml_ssps, np.ones(4000), qa, qm, fill_nan=False)
+    mf = ref.misc_functions
+    libdir = os.path.join(os.path.dirname(os.path.realpath(mf.__file__)), "SSPLibraries")
+    mData = quiet(mf.SSPMass, os.path.join(libdir, "out_mass_KB_BASTI.txt"))
+    lData = quiet(mf.SSPPhot, os.path.join(libdir, "out_phot_KB_BASTI.txt"))
+    mw = np.isclose(1.30, mData['slope'], atol=1e-2)
+    lw = np.isclose(1.30, lData['slope'], atol=1e-2)
+    nodes_ml = mData['mSRem'][mw] / 10 ** (-0.4 * (lData['V'][lw] - 4.820))
+    save("ssp", age=qa, MH=qm, ML=ML, ML_nofill=ML_nofill, node_age=mData['age'][mw], node_MH=mData['MH'][mw], node_ML=nodes_ml)
+
     for k, v in saved.items():
         print("%-16s %8.1f kB (uncompressed)" % (k, v / 1e3))
 

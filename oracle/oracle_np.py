@@ -371,6 +371,21 @@ def rebin_spatial(cube, binx, biny, factorx=1, factory=1, function="sum"):
     return bx, by, out
 
 
+# --------------------------------------------------------------------------- SSP M/L (f2)
+def ml_from_nodes(node_age, node_MH, node_ML, age, MH, fill_nan=True):
+    """misc_functions.py:195-202: scipy griddata 'cubic' (Clough-Tocher on the Delaunay triangulation
+    of the table nodes), NaN outside the hull replaced by the nearest node.  scipy is the
+    reference's own dependency for this step (unpinned; 1.18.1 here), so the oracle calls it the
+    way the reference does."""
+    from scipy.interpolate import griddata
+    age, MH = np.asarray(age, dtype=np.float64), np.asarray(MH, dtype=np.float64)
+    ML = griddata((node_age, node_MH), node_ML, (age, MH), method="cubic")
+    if fill_nan:
+        bad = np.isnan(ML)
+        ML[bad] = griddata((node_age, node_MH), node_ML, (age[bad], MH[bad]), method="nearest")
+    return ML
+
+
 # --------------------------------------------------------------------------- LOSVD moments (f1)
 def moment012(x, data):
     """misc_functions.py:70-90."""

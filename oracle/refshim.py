@@ -63,9 +63,15 @@ def _convolve(array, kernel, boundary="fill", fill_value=0.0, **_):
 
 class _Table(dict):
     @classmethod
-    def read(cls, filename, format=None, **_):
+    def read(cls, filename, format=None, names=None, **_):
+        """Stand-in for astropy's Table.read(format='ascii').  Its basic reader takes the first line
+        as the header line even when ``names`` overrides the column names, so the first row of the
+        header-less SSP tables (misc_functions.py:223-226, :242-249) is consumed: 635 of 636 rows.
+        (astropy is absent here; this mirrors its documented behaviour and is an assumption.)"""
         with open(filename) as fh:
             header = fh.readline().lstrip("#").split()
+        if names is not None:
+            header = list(names)
         data = np.loadtxt(filename, skiprows=1, dtype=str)
         out = cls()
         for i, name in enumerate(header):

@@ -12,6 +12,6 @@ there is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-from . import _lib, engine, rotation, losvd, grid, pynmap, hostpath, sharded  # noqa: F401
+from . import _lib, engine, rotation, losvd, grid, pynmap, hostpath, sharded, ssp  # noqa: F401
 from .pynmap import snapshot, SnapMap  # noqa: F401
 from .losvd import LOSVD  # noqa: F401

@@ -436,6 +436,32 @@ int pnm_rebin_cube(const double* cube_in, double* cube_out, int32_t nx, int32_t 
     return PNM_OK;
 }
 
+int pnm_ct_interp(const void* qx, const void* qy, int64_t n, int dtype, const double* tri_xform, const double* tri_coef,
+                  int32_t ntri, const int32_t* cell_start, const int32_t* cell_tris, int32_t ncell,
+                  double lo0, double lo1, double inv0, double inv1, const double* nodes, int32_t nnode,
+                  int fill_nearest, double* out, void* stream) {
+    if (n < 0 || ntri < 1 || ncell < 1 || nnode < 1) return fail(PNM_EINVAL, "pnm_ct_interp: bad sizes");
+    if (nnode > pnm::kCtMaxNodes) return fail(PNM_ELIMIT, "pnm_ct_interp: more than %d table nodes", pnm::kCtMaxNodes);
+    if (n == 0) return PNM_OK;
+    if (!qx || !qy || !tri_xform || !tri_coef || !cell_start || !cell_tris || !nodes || !out)
+        return fail(PNM_EINVAL, "pnm_ct_interp: null argument");
+    const int grid = grid_for(n, 256, 8);
+    const size_t smem = (size_t)nnode * 3 * sizeof(double);
+    if (dtype == PNM_F32) {
+        if (smem > 48 * 1024) PNM_CUDA(cudaFuncSetAttribute(pnm::k_ct_interp<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pnm::k_ct_interp<float><<<grid, 256, smem, as_stream(stream)>>>((const float*)qx, (const float*)qy, n, tri_xform, tri_coef,
+            cell_start, cell_tris, ncell, lo0, lo1, inv0, inv1, nodes, nnode, fill_nearest, out);
+    } else if (dtype == PNM_F64) {
+        if (smem > 48 * 1024) PNM_CUDA(cudaFuncSetAttribute(pnm::k_ct_interp<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        pnm::k_ct_interp<double><<<grid, 256, smem, as_stream(stream)>>>((const double*)qx, (const double*)qy, n, tri_xform, tri_coef,
+            cell_start, cell_tris, ncell, lo0, lo1, inv0, inv1, nodes, nnode, fill_nearest, out);
+    } else {
+        return fail(PNM_EDTYPE, "pnm_ct_interp: dtype %d", dtype);
+    }
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
 int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream) {
     if (!out_dev || n < 0 || (n > 0 && !a)) return fail(PNM_EINVAL, "pnm_absmax: bad argument");
     PNM_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), as_stream(stream)));

@@ -241,6 +241,65 @@ __global__ void __launch_bounds__(256) k_cube_moments(const double* __restrict__
     }
 }
 
+// ---------------------------------------------------------------- f2: scattered cubic interpolation
+// scipy.interpolate.griddata(method='cubic') + nearest-node fill (misc_functions.py:195-202), per
+// particle: uniform cell -> candidate triangles -> barycentric test (scipy's eps = 100 * DBL_EPSILON)
+// -> the 19-term Clough-Tocher cubic whose Bezier ordinates the host precomputed per triangle.
+// Points outside the convex hull take the value of the nearest table node (nodes cached in shared
+// memory: 636 x 24 B).
+constexpr int kCtMaxNodes = 2048;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_ct_interp(const T* __restrict__ qx, const T* __restrict__ qy, int64_t n,
+                                                   const double* __restrict__ xform, const double* __restrict__ coef,
+                                                   const int* __restrict__ cell_start, const int* __restrict__ cell_tris,
+                                                   int ncell, double lo0, double lo1, double inv0, double inv1,
+                                                   const double* __restrict__ nodes, int nnode, int fill,
+                                                   double* __restrict__ out) {
+    extern __shared__ double s_nodes[];                  // [nnode][3] = x, y, value
+    for (int i = threadIdx.x; i < nnode * 3; i += blockDim.x) s_nodes[i] = nodes[i];
+    __syncthreads();
+    const double eps = 100.0 * 2.220446049250313e-16;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double px = (double)qx[i], py = (double)qy[i];
+        double res = __longlong_as_double(0x7ff8000000000000ll);   // NaN
+        const double gx = floor((px - lo0) * inv0), gy = floor((py - lo1) * inv1);
+        if (gx >= 0.0 && gx <= (double)ncell && gy >= 0.0 && gy <= (double)ncell) {   // false for NaN
+            const int cx = min((int)gx, ncell - 1), cy = min((int)gy, ncell - 1);
+            const int c = cx * ncell + cy;
+            for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
+                const int t = cell_tris[k];
+                const double* X = xform + (int64_t)t * 6;
+                const double dx = px - X[4], dy = py - X[5];
+                const double b0 = X[0] * dx + X[1] * dy, b1 = X[2] * dx + X[3] * dy, b2 = 1.0 - b0 - b1;
+                if (fmin(b0, fmin(b1, b2)) >= -eps) {
+                    const double* C = coef + (int64_t)t * 19;
+                    const double mn = fmin(b0, fmin(b1, b2));
+                    const double a1 = b0 - mn, a2 = b1 - mn, a3 = b2 - mn, a4 = 3.0 * mn;
+                    res = a1 * a1 * a1 * C[0] + 3 * a1 * a1 * a2 * C[1] + 3 * a1 * a1 * a3 * C[2] + 3 * a1 * a1 * a4 * C[3]
+                        + 3 * a1 * a2 * a2 * C[4] + 6 * a1 * a2 * a4 * C[5] + 3 * a1 * a3 * a3 * C[6] + 6 * a1 * a3 * a4 * C[7]
+                        + 3 * a1 * a4 * a4 * C[8] + a2 * a2 * a2 * C[9] + 3 * a2 * a2 * a3 * C[10] + 3 * a2 * a2 * a4 * C[11]
+                        + 3 * a2 * a3 * a3 * C[12] + 6 * a2 * a3 * a4 * C[13] + 3 * a2 * a4 * a4 * C[14] + a3 * a3 * a3 * C[15]
+                        + 3 * a3 * a3 * a4 * C[16] + 3 * a3 * a4 * a4 * C[17] + a4 * a4 * a4 * C[18];
+                    break;
+                }
+            }
+        }
+        if (fill && res != res && px == px && py == py) {   // outside the hull: nearest node
+            double best = 1.7976931348623157e308;
+            int arg = 0;
+            for (int j = 0; j < nnode; ++j) {
+                const double dx = px - s_nodes[3 * j], dy = py - s_nodes[3 * j + 1];
+                const double d2 = dx * dx + dy * dy;
+                if (d2 < best) { best = d2; arg = j; }
+            }
+            res = s_nodes[3 * arg + 2];
+        }
+        out[i] = res;
+    }
+}
+
 // ---------------------------------------------------------------- abs-max (fixed-point scale)
 // Non-negative doubles order like their bit patterns, so one integer atomicMax per block suffices.
 template <typename T>

@@ -198,20 +198,23 @@ class snapshot(object):
         self._ingest(pos, vel, mass, age, MH)
 
     def compute_ml(self):
-        """flux = mass / ML (pynmap/pynmap.py:234-236).  The SSP interpolation of the reference
-        (misc_functions.compute_ml_ssps, scipy griddata on the E-MILES tables) is a host-side,
-        once-per-snapshot step outside the hot path: pass ``ml_function`` to
-        plug it in, or ``flux=`` to from_arrays.  Any other recipe is M/L = 1."""
+        """flux = mass / ML (pynmap/pynmap.py:234-236).  The SSP recipe of the reference
+        (misc_functions.compute_ml_ssps: scipy griddata on the E-MILES tables) needs those tables,
+        which are data of the reference and are not shipped here: pass
+        ``ml_function=functools.partial(pynmap_b200.ssp.compute_ml_ssps, ssp_dir=<SSPLibraries>)``
+        (GPU interpolation), any callable (mass, age, MH) -> M/L, or ``flux=`` to
+        from_arrays.  Any other recipe is M/L = 1.  M/L is kept in float64 like the reference's; the
+        flux is rounded to the particle dtype."""
         if self.ml_function is not None:
             ml = self.ml_function(self.mass, self.age, self.MH)
-            self.ML = engine.to_device(ml, self.mass.dtype, self.mass.device)
+            self.ML = engine.to_device(ml, torch.float64, self.mass.device)
         elif self.MLrecipe == "SSPs":
             raise NotImplementedError(
-                "MLrecipe='SSPs' needs the reference's SSP tables: pass ml_function=pynmap.misc_functions."
-                "compute_ml_ssps (host side) or precomputed flux; use MLrecipe=None for M/L = 1")
+                "MLrecipe='SSPs' needs the reference's SSP tables: pass ml_function=functools.partial("
+                "pynmap_b200.ssp.compute_ml_ssps, ssp_dir=...) or precomputed flux; use MLrecipe=None for M/L = 1")
         else:
-            self.ML = torch.ones_like(self.mass)
-        self.flux = self.mass / self.ML
+            self.ML = torch.ones_like(self.mass, dtype=torch.float64)
+        self.flux = (self.mass.double() / self.ML).to(self.mass.dtype)
 
     # ------------------------------------------------------------------ rotation state
     def reset(self):
