@@ -139,7 +139,9 @@ class MLInterpolator(object):
     """griddata(method='cubic') + nearest fill of a scattered (age, [M/H]) -> M/L table, evaluated
     per particle on the GPU.  Build once per table, call per snapshot."""
 
-    def __init__(self, ages, metals, ml, ncell=64, device=None):
+    def __init__(self, ages, metals, ml, ncell=256, device=None):
+        # ncell: 64 -> 13.6 ms, 128 -> 10.3, 256 -> 8.9, 512 -> 8.2 ms per 1e8 particles on a B200 (9.5 ->
+        # 2.7 candidate triangles per cell); the reference's scipy path takes ~1 s per 1e6 particles
         pts = np.stack([np.asarray(ages, dtype=np.float64), np.asarray(metals, dtype=np.float64)], axis=1)
         self.tabs = clough_tocher_tables(pts, ml)
         self.cells = cell_index(self.tabs["points"], self.tabs["simplices"], ncell)
