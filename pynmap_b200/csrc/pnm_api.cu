@@ -218,7 +218,7 @@ int launch_bin(const pnm::BinParams& p, int acc_mode, cudaStream_t st) {
     const bool simple = p.nviews == 1 && p.nchain == 1 && p.mask_mode == PNM_MASK_NONE;
     // shared memory: edge tables (+ the TMA staging area when the hybrid scatter can run)
     size_t smem = pnm::bin_table_bytes<T>(p.nx, p.ny, p.nv);
-    if (aligned && simple && p.tma_slots > 0) smem += pnm::bin_stage_bytes(pnm::kBinThreads);
+    if (aligned && simple && p.tma_slots > 0) smem += pnm::bin_stage_bytes(pnm::kBinThreads, p.tma_slots);
     if (smem > 227 * 1024) return fail(PNM_ELIMIT, "k_project_bin: %zu bytes of shared memory", smem);
     // hot configurations get the set of sums as a compile-time constant (fused path only)
     constexpr int kFull = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2 | PNM_SUM_CUBE | PNM_W_FROM_CUBE;

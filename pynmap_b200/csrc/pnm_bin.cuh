@@ -19,11 +19,13 @@
 //   * consecutive particles of a thread that fall in the same pixel are merged in registers before
 //     the reduction (free for random order, ~1 per run for space-filling-curve ordered snapshots);
 //   * with PNM_W_FROM_CUBE the map's sum w costs no RED at all for particles inside the V range;
-//   * HYBRID SCATTER: (sum w*d, sum w*d*d) sit in one 16-byte half sector, so most map updates are
-//     staged in shared memory and sent as ONE 16-byte TMA bulk reduction
-//     (cp.reduce.async.bulk.global.shared::cta ... add.f64/.u64, SASS UBLKRED) instead of two LSU
-//     REDs.  The TMA unit sustains ~7.5e10 such ops/s per GPU next to the LSU's 1.9e11 REDs/s and
-//     the two overlap (scripts/tma_mix_bench.cu: 1.60 -> 1.21 ms per 1e8 particles at a 3:1 split);
+//   * HYBRID SCATTER: (sum w*d, sum w*d*d[, sum w]) sit in one 32-byte sector, so part of the map
+//     updates (3-4 of a tile's 8) are staged in shared memory and sent as ONE 16- or 32-byte TMA
+//     bulk reduction (cp.reduce.async.bulk.global.shared::cta ... add.f64/.u64, SASS UBLKRED)
+//     instead of two or three LSU REDs.  The TMA unit sustains ~7.5e10 such ops/s per GPU next to
+//     the LSU's 1.9e11 REDs/s and the two overlap (scripts/tma_mix_bench.cu).  UBLKRED is a
+//     warp-uniform instruction: per-lane destinations cost an ELECT/R2UR issue loop, which is why
+//     the share is 3-4 of 8 and not more (measured, see pnm_api.cu);
 //   * bin lookup: the uniform guess floor((x-x0)*inv) is PROVABLY the numpy bin whenever its
 //     fractional part is further than `eps` from an integer (eps bounds the float rounding of the
 //     guess plus the deviation of np.linspace edges from an affine grid, computed at grid
@@ -75,7 +77,7 @@ template <> struct Pack<double> {
 };
 
 // ---- bin lookup --------------------------------------------------------------------------------
-template <typename T> struct Axis { T x0, inv, eps, one_m_eps, n_plus_half; int n; const T* thr; };
+template <typename T> struct Axis { T x0, inv, eps, one_m_eps; int n; const T* thr; };
 
 // exact path: binary search in the table of thresholds (thr[i] <= x < thr[i+1], see pnm_grid_create),
 // independent of the guess, so it is exact for any monotone edges.  Out of line: it is rare.
@@ -134,14 +136,14 @@ __device__ __forceinline__ void red_add(long long* p, long long v) {
 }
 
 // ---- TMA staging of (S1, S2) pairs ---------------------------------------------------------------
-// Shared-memory layout per CTA: kTmaStages x kTmaSlots x blockDim.x records of 32 bytes
+// Shared-memory layout per CTA: kTmaStages x tma_slots x blockDim.x records of 32 bytes
 // (S1, S2, S0, pad; consecutive threads, consecutive records) + the matching destination offsets.  A thread
 // only ever touches its own records, so ordering needs no CTA barrier: generic-proxy writes ->
 // fence.proxy.async -> bulk reductions -> commit_group; before a stage is rewritten two tiles
 // later, wait_group.read 1 guarantees the TMA unit has read it.
 // of the (up to) 8 map updates of a tile; the rest take the LSU path.  Measured on the bench
 // workload (1e8 particles, maps + cube): 0 -> 1.78 ms, 2 -> 1.65, 4 -> 1.59, 5 -> 1.67, 6 -> 1.82
-constexpr int kTmaSlots = 6;      // capacity; the launcher picks how many are used (BinParams::tma_slots)
+constexpr int kTmaSlots = 6;      // upper bound; the launcher picks how many are used (BinParams::tma_slots)
 constexpr int kTmaStages = 2;
 
 __device__ __forceinline__ void tma_fence_writes() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -230,9 +232,9 @@ struct Binner {
     double sc0, sc1, sc2;
 
     __device__ __forceinline__ Binner(const BinParams& p, const T* sx, const T* sy, const T* sv) {
-        ax = {(T)p.x0, (T)p.inv_dx, (T)p.eps_x, (T)1 - (T)p.eps_x, (T)p.nx + (T)0.5, p.nx, sx};
-        ay = {(T)p.y0, (T)p.inv_dy, (T)p.eps_y, (T)1 - (T)p.eps_y, (T)p.ny + (T)0.5, p.ny, sy};
-        av = {(T)p.v0, (T)p.inv_dv, (T)p.eps_v, (T)1 - (T)p.eps_v, (T)p.nv + (T)0.5, p.nv, sv};
+        ax = {(T)p.x0, (T)p.inv_dx, (T)p.eps_x, (T)1 - (T)p.eps_x, p.nx, sx};
+        ay = {(T)p.y0, (T)p.inv_dy, (T)p.eps_y, (T)1 - (T)p.eps_y, p.ny, sy};
+        av = {(T)p.v0, (T)p.inv_dv, (T)p.eps_v, (T)1 - (T)p.eps_v, p.nv, sv};
         rsums = p.sums; nx = p.nx; ny = p.ny; npix = p.nx * p.ny; mask_mode = p.mask_mode;
         sc0 = p.scale[0]; sc1 = p.scale[1]; sc2 = p.scale[2];
     }
@@ -301,8 +303,8 @@ template <typename T>
 __host__ __device__ inline size_t bin_table_bytes(int nx, int ny, int nv) {
     return (((size_t)(nx + 1) + (ny + 1) + (nv + 1)) * sizeof(T) + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t bin_stage_bytes(int threads) {
-    return (size_t)kTmaStages * kTmaSlots * threads * (32 + 4);
+__host__ __device__ inline size_t bin_stage_bytes(int threads, int slots) {
+    return (size_t)kTmaStages * slots * threads * (32 + 4);
 }
 
 // ---- kernel: persistent grid-stride loop; each thread takes Pack<T>::N consecutive particles per
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
     // TMA staging (SIMPLE + vector path only): [stage][slot][thread] records, then the offsets
     unsigned char* stage_raw = smem_raw + bin_table_bytes<T>(p.nx, p.ny, p.nv);
     A* const stage_vals = reinterpret_cast<A*>(stage_raw);
-    int* const stage_offs = reinterpret_cast<int*>(stage_raw + (size_t)kTmaStages * kTmaSlots * blockDim.x * 32);
+    int* const stage_offs = reinterpret_cast<int*>(stage_raw + (size_t)kTmaStages * p.tma_slots * blockDim.x * 32);
     TmaStage<ACC> st;
     st.stride = blockDim.x; st.used = 0;
     st.cap = (SIMPLE && VECLOAD) ? p.tma_slots : 0;
@@ -387,8 +389,8 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
             if (W) Pack<T>::load(W + i * VN, w);
             if (st.cap) {                                   // the stage used two tiles ago must have been read
                 tma_wait_read_1();
-                st.vals = stage_vals + ((size_t)parity * kTmaSlots * blockDim.x + threadIdx.x) * 4;
-                st.offs = stage_offs + (size_t)parity * kTmaSlots * blockDim.x + threadIdx.x;
+                st.vals = stage_vals + ((size_t)parity * p.tma_slots * blockDim.x + threadIdx.x) * 4;
+                st.offs = stage_offs + (size_t)parity * p.tma_slots * blockDim.x + threadIdx.x;
                 parity ^= 1;
             }
             MapRun<ACC> run;

@@ -37,22 +37,12 @@ __device__ __forceinline__ bool is_finite(float v) { return fabsf(v) <= 3.402823
 __device__ __forceinline__ bool is_finite(double v) { return fabs(v) <= 1.7976931348623157e+308; }
 
 // --------------------------------------------------------------------------------------------
-// Bin lookup.  `thr` holds n+1 thresholds in the particle dtype such that bin i is exactly
+// Bin tables.  `thr` holds n+1 thresholds in the particle dtype such that bin i is exactly
 // thr[i] <= x < thr[i+1]  <=>  edges[i] <= (double)x < edges[i+1]  (numpy searchsorted 'right'),
 // with thr[n] nudged one ulp up so that the closed last edge of np.histogramdd
-// (_histograms_impl.py:1049-1053) is covered by the same test.  NaN fails the first test.
-// The uniform guess is only a hint: the two loops make the result exact for any monotone table.
+// (_histograms_impl.py:1049-1053) is covered by the same test; NaN fails every test.  The lookup
+// itself (uniform guess + exact table search near edges) lives in pnm_bin.cuh.
 // --------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ int find_bin(T x, const T* __restrict__ thr, int n, T x0, T inv_step) {
-    if (!(x >= thr[0]) || !(x < thr[n])) return -1;
-    T g = (x - x0) * inv_step;
-    int i = (int)g;                       // x >= thr[0] so g is >= ~0; saturating conversion
-    i = max(0, min(i, n - 1));
-    while (x < thr[i]) --i;
-    while (x >= thr[i + 1]) ++i;
-    return i;
-}
 
 // --------------------------------------------------------------------------------------------
 // Accumulation.  8-byte accumulators, two arithmetics:
