@@ -16,6 +16,7 @@
  *   pnm_finalize_cube     weights-histogram -> float64 cube    pynmap/grid.py:259
  *   pnm_smooth_cube       astropy convolve per velocity slice  pynmap/losvd.py:127-135
  *   pnm_cube_moments      moment012 per spaxel                 pynmap/losvd.py:41-51, misc_functions.py:70-90
+ *   pnm_fit_gh            fitgh (mpfit) per spaxel             pynmap/losvd.py:53-67, fit_losvd.py:57-235
  *   pnm_absmax            (new) bound for the fixed-point scale
  *   pnm_project_host      snapshot.rotate + velocity_moments + create_losvds from HOST arrays
  *                                                              pynmap/pynmap.py:246-285, :319-340, :439-455
@@ -191,6 +192,25 @@ int pnm_ct_interp(const void* qx, const void* qy, int64_t n, int dtype,
 int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv,
                      const double* binv_dev, double empty_m2,
                      double* mom0, double* mom1, double* mom2, void* stream);
+
+/* ---- f4: Gauss-Hermite fit of every spaxel (losvd.py:53-67, fit_losvd.py:57-235) -------------
+ * For each of the nspax profiles cube[s][0..nv) minimise sum(((d - A u(p)) / err)^2) over
+ * p = (V, S, h3 .. h_deg_gh) with A = sum((d/err)^2) / sum((d/err)(u/err)) re-solved at every
+ * evaluation (fit_losvd.py:25-54, :178-185), u = gausshermite(binv, [1, p]) (misc_functions.py:
+ * 15-68); start at the profile's moments with h_n = guess_h; box limits [lo_v, hi_v], [lo_s, hi_s],
+ * +-lim_h (fit_losvd.py:157-165).  Bounded Levenberg-Marquardt with an analytic Jacobian; the limits
+ * are handled and the convergence tests (ftol, xtol, gtol, maxiter) and status codes defined as in
+ * utils/mpfit.py:1074-1094, :1171-1230, :1303-1322.  err_dev may be NULL (unit errors).
+ *   gh      [deg_gh + 1][nspax]  (I, V, S, h3 ..)      bestfit [nspax][nv] or NULL
+ *   status  [nspax]  1..4 converged, 5 maxiter, -16 non-finite (e.g. all-zero profile: I = NaN and
+ *                    p = start values, as the reference returns), 0 start values outside the limits
+ *                    (the reference raises; gh = NaN)
+ *   niter   [nspax]  accepted steps + 1 (mpfit's niter)       chi2 [nspax] final sum of squares
+ * deg_gh in 2..6.                                                                                */
+int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t nv, const double* binv_dev,
+               int32_t deg_gh, double lo_v, double hi_v, double lo_s, double hi_s, double lim_h,
+               double guess_h, double empty_m2, double ftol, double xtol, double gtol, int32_t maxiter,
+               double* gh, double* bestfit, int32_t* status, int32_t* niter, double* chi2, void* stream);
 
 /* ---- max |a[i]| over n elements -> out_dev[0] (float64, device); used to pick FIXED scales -- */
 int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream);

@@ -176,8 +176,64 @@ def main():
     nodes_ml = mData['mSRem'][mw] / 10 ** (-0.4 * (lData['V'][lw] - 4.820))
     save("ssp", age=qa, MH=qm, ML=ML, ML_nofill=ML_nofill, node_age=mData['age'][mw], node_MH=mData['MH'][mw], node_ML=nodes_ml)
 
+    make_fit_golden(ref, save)
+
     for k, v in saved.items():
         print("%-16s %8.1f kB (uncompressed)" % (k, v / 1e3))
+
+
+def make_fit_golden(ref, save):
+    """Row f4: the reference's own Gauss-Hermite fits (fit_losvd.fitgh -> mpfit, fit_losvd.py:84-235;
+    LOSVD.fitlosvd, losvd.py:53-67) on noisy synthetic profiles and on a cube of a toy snapshot."""
+    fl, mf = ref.fit_losvd, ref.misc_functions
+    edges = np.linspace(-500.0, 500.0, 65)
+    x = 0.5 * (edges[1:] + edges[:-1])
+    rng = np.random.default_rng(77)
+
+    def run(profiles, deg, errs=None):
+        gh = np.zeros((len(profiles), deg + 1))
+        status, niter, fnorm = (np.zeros(len(profiles), dtype=t) for t in (np.int32, np.int32, np.float64))
+        best = np.zeros_like(profiles)
+        for i, d in enumerate(profiles):
+            with np.errstate(all="ignore"):
+                gh[i], res, best[i] = quiet(fl.fitgh, x, d, deg_gh=deg, err=None if errs is None else errs[i],
+                                            verbose=False)
+            status[i], niter[i], fnorm[i] = res.status, res.niter, res.fnorm
+        return gh, status, niter, fnorm, best
+
+    out = {"x": x}
+    for deg, count in ((4, 96), (2, 16), (3, 16), (5, 16), (6, 16)):
+        truth = np.zeros((count, 7))
+        truth[:, 0] = rng.uniform(2.0, 200.0, count)
+        truth[:, 1] = rng.uniform(-300.0, 300.0, count)
+        truth[:, 2] = rng.uniform(20.0, 180.0, count)
+        truth[:, 3:] = rng.uniform(-0.25, 0.25, (count, 4))       # beyond +-0.2: fits end pegged at a limit
+        prof = np.stack([rng.poisson(np.maximum(mf.gausshermite(x, t[:deg + 1]), 0.0)).astype(np.float64)
+                         for t in truth])
+        if deg == 4:
+            prof[-1] = 0.0                                        # all-zero spaxel: I = NaN, status -16
+        gh, status, niter, fnorm, best = run(prof, deg)
+        out.update({"data%d" % deg: prof, "gh%d" % deg: gh, "status%d" % deg: status, "niter%d" % deg: niter,
+                    "fnorm%d" % deg: fnorm, "best%d" % deg: best})
+    # with an error array (fit_losvd.py:180-185, :442-446)
+    truth = np.stack([rng.uniform(20.0, 200.0, 16), rng.uniform(-200.0, 200.0, 16), rng.uniform(40.0, 150.0, 16),
+                      rng.uniform(-0.15, 0.15, 16), rng.uniform(-0.15, 0.15, 16)], 1)
+    prof = np.stack([rng.poisson(np.maximum(mf.gausshermite(x, t), 0.0)).astype(np.float64) for t in truth])
+    errs = np.sqrt(np.maximum(prof, 1.0))
+    gh, status, niter, fnorm, best = run(prof, 4, errs)
+    out.update(data_err=prof, err=errs, gh_err=gh, status_err=status, niter_err=niter, fnorm_err=fnorm, best_err=best)
+
+    # LOSVD.fitlosvd on a populated cube
+    pos, vel, mass = toy_snapshot(60000, 5, np.float64)
+    lim = [-3.0, 3.0, -3.0, 3.0]
+    lv = quiet(ref.grid.points_2losvds, pos[:, 0], pos[:, 1], vel[:, 2], weights=mass, limXY=lim, nXY=8,
+               limV=[-450.0, 450.0], nV=36)
+    with np.errstate(all="ignore"):
+        quiet(lv.fitlosvd, degree=4, verbose=False)
+    out.update(cube=lv.losvd, cube_binv=lv.binv, cube_GH=lv.GH, cube_bestfit=lv.bestfit,
+               cube_status=np.array([r.status for r in lv.resfit], dtype=np.int32).reshape(8, 8),
+               cube_fnorm=np.array([r.fnorm for r in lv.resfit]).reshape(8, 8))
+    save("fit", **out)
 
 
 def _matrix(rot, pa, inc):

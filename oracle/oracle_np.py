@@ -423,3 +423,73 @@ def project_path(pos, vel, mass, PA, inclination, limXY, nXY, limV=None, nV=None
         sample = np.hstack((x.reshape(n, 1), y.reshape(n, 1), vz.reshape(n, 1)))
         cube = np.histogramdd(sample, bins=(ex, ey, ev), weights=mass)[0]
     return s0, V, S, cube
+
+
+# --------------------------------------------------------------------------- Gauss-Hermite fit
+# Row f4.  The *objective* below restates the reference exactly (misc_functions.py:15-68,
+# fit_losvd.py:25-54, :178-185, :456-459); the optimiser does not: the reference drives it with a
+# vendored MINPACK port (utils/mpfit.py:599-2326, finite-difference Jacobian), which is
+# tolerance-defined, so the checkers here are (a) the reference's own fitted parameters, stored as
+# golden vectors by oracle/make_golden.py, (b) scipy's bounded trust-region solver on the restated
+# objective, and (c) first-order optimality of the restated objective.
+def gausshermite(vbin, gh):
+    """misc_functions.py:15-68 (note its recursion drops the sqrt(i) factor of the textbook one)."""
+    gh = np.asarray(gh, dtype=np.float64)
+    degree = len(gh) - 1
+    if degree < 2 or gh[2] == 0.0:
+        return vbin * 0.0
+    w = (vbin - gh[1]) / gh[2]
+    w2 = w * w
+    h_prev = (2.0 * w2 - 1.0) / np.sqrt(2.0)
+    h_cur = (2.0 * w2 - 3.0) * w / np.sqrt(3.0)
+    h_use = h_cur
+    var = 1.0
+    for i in range(3, degree + 1):
+        var = var + gh[i] * h_use
+        h_use = (np.sqrt(2.0) * h_cur * w - h_prev) / np.sqrt(i + 1.0)
+        h_prev = h_cur
+        h_cur = h_use
+    return gh[0] * var * np.exp(-w2 / 2.0)
+
+
+def gh_amplitude(data, ufit, err=None):
+    """fit_losvd.py:25-54: sum(dn*dn) / sum(dn*fn) -- not the least-squares amplitude."""
+    if err is None:
+        err = np.ones_like(data)
+    err = np.where(err == 0.0, 1.0, err)
+    dn = data / err
+    fn = ufit / err
+    with np.errstate(invalid="ignore", divide="ignore"):
+        return np.sum(dn * dn) / np.sum(dn * fn)
+
+
+def gh_residuals(p, x, data, err=None):
+    """fit_losvd.py:178-185 (mpfitfun): amplitude re-solved at every evaluation."""
+    gh = np.concatenate(([1.0], p))
+    gh[0] = gh_amplitude(data, gausshermite(x, gh), err)
+    res = data - gausshermite(x, gh)
+    return res if err is None else res / err
+
+
+def gh_guess_and_limits(x, data, deg_gh):
+    """fit_losvd.py:157-165: start at the moments, h_n = 0.02, box limits from the axis."""
+    m0, m1, m2 = moment012(x, data)
+    p0 = np.full(deg_gh, 0.02)
+    p0[:2] = (m1, m2)
+    lo = np.full(deg_gh, -0.2)
+    lo[:2] = (np.min(x), np.min(np.diff(x)) / 3.0)
+    hi = np.full(deg_gh, 0.2)
+    hi[:2] = (np.max(x), (np.max(x) - np.min(x)) / 3.0)
+    return p0, lo, hi
+
+
+def fit_gh_scipy(x, data, deg_gh=4, err=None):
+    """Independent checker: scipy's bounded trust-region least squares on the restated objective.
+    Returns ([I, V, S, h3..], chi2)."""
+    from scipy.optimize import least_squares
+    p0, lo, hi = gh_guess_and_limits(x, data, deg_gh)
+    sol = least_squares(gh_residuals, np.clip(p0, lo, hi), bounds=(lo, hi), args=(x, data, err),
+                        x_scale="jac", ftol=1e-14, xtol=1e-14, gtol=1e-14, max_nfev=2000)
+    gh = np.concatenate(([1.0], sol.x))
+    gh[0] = gh_amplitude(data, gausshermite(x, gh), err)
+    return gh, float(np.sum(gh_residuals(sol.x, x, data, err) ** 2))

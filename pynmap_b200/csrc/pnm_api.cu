@@ -9,6 +9,7 @@
 
 #include "pnm_bin.cuh"
 #include "pnm_post.cuh"
+#include "pnm_fit.cuh"
 
 namespace {
 
@@ -419,6 +420,36 @@ int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv, con
     const int nspax = nx * ny;
     const int grid = (nspax * 32 + 255) / 256;
     pnm::k_cube_moments<<<grid, 256, 0, as_stream(stream)>>>(cube, nspax, nv, binv_dev, empty_m2, mom0, mom1, mom2);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t nv, const double* binv_dev,
+               int32_t deg_gh, double lo_v, double hi_v, double lo_s, double hi_s, double lim_h, double guess_h,
+               double empty_m2, double ftol, double xtol, double gtol, int32_t maxiter, double* gh, double* bestfit,
+               int32_t* status, int32_t* niter, double* chi2, void* stream) {
+    if (nspax < 0 || nv < 1 || maxiter < 0) return fail(PNM_EINVAL, "pnm_fit_gh: bad sizes");
+    if (deg_gh < 2 || deg_gh > 6) return fail(PNM_ELIMIT, "pnm_fit_gh: deg_gh must be in 2..6 (got %d)", deg_gh);
+    if (nv <= deg_gh) return fail(PNM_EINVAL, "pnm_fit_gh: number of parameters must not exceed data");
+    if (nspax == 0) return PNM_OK;
+    if (!cube || !binv_dev || !gh || !status || !niter || !chi2) return fail(PNM_EINVAL, "pnm_fit_gh: null argument");
+    if (!(lo_v <= hi_v) || !(lo_s <= hi_s) || !(lo_s > 0.0) || !(lim_h >= 0.0))
+        return fail(PNM_EINVAL, "pnm_fit_gh: parameter limits are not consistent");
+    pnm::FitParams P;
+    P.cube = cube; P.err = err_dev; P.binv = binv_dev; P.nv = nv; P.nspax = nspax;
+    P.lo_v = lo_v; P.hi_v = hi_v; P.lo_s = lo_s; P.hi_s = hi_s; P.lim_h = lim_h; P.guess_h = guess_h;
+    P.empty_m2 = empty_m2; P.ftol = ftol; P.xtol = xtol; P.gtol = gtol; P.maxiter = maxiter;
+    P.gh = gh; P.bestfit = bestfit; P.status = status; P.niter = niter; P.chi2 = chi2;
+    const unsigned grid = (unsigned)((nspax + pnm::kFitWarps - 1) / pnm::kFitWarps);
+    const int threads = pnm::kFitWarps * 32;
+    cudaStream_t s = as_stream(stream);
+    switch (deg_gh) {
+        case 2: pnm::k_fit_gh<2><<<grid, threads, 0, s>>>(P); break;
+        case 3: pnm::k_fit_gh<3><<<grid, threads, 0, s>>>(P); break;
+        case 4: pnm::k_fit_gh<4><<<grid, threads, 0, s>>>(P); break;
+        case 5: pnm::k_fit_gh<5><<<grid, threads, 0, s>>>(P); break;
+        default: pnm::k_fit_gh<6><<<grid, threads, 0, s>>>(P); break;
+    }
     PNM_CUDA(cudaGetLastError());
     return PNM_OK;
 }

@@ -391,6 +391,37 @@ def cube_moments(cube, binv):
     return m0, m1, m2
 
 
+def fit_gh(profiles, binv, deg_gh=4, err=None, ftol=1e-10, xtol=1e-10, gtol=1e-10, maxiter=200,
+           want_bestfit=True):
+    """pnm_fit_gh on ``profiles`` (..., nv): Gauss-Hermite fit of every profile (row f4;
+    fit_losvd.py:84-235 with its default limits and start values, :157-165).  Returns
+    (gh (deg_gh+1, ...), bestfit (..., nv) or None, status, niter, chi2) as device tensors."""
+    profiles = profiles.contiguous()
+    lead, nv = tuple(profiles.shape[:-1]), int(profiles.shape[-1])
+    nspax = int(np.prod(lead)) if lead else 1
+    binv = np.asarray(binv, dtype=np.float64).ravel()
+    if binv.size != nv:
+        raise ValueError("fit_gh: the velocity axis has {} points, the profiles {}".format(binv.size, nv))
+    dev = profiles.device
+    bv = to_device(binv, torch.float64, dev)
+    dx = np.diff(binv)
+    lo_v, hi_v = float(np.min(binv)), float(np.max(binv))                 # fit_losvd.py:160-163
+    lo_s, hi_s = float(np.min(dx) / 3.0), float((hi_v - lo_v) / 3.0)
+    if err is not None:
+        err = err.contiguous()
+        if tuple(err.shape) != tuple(profiles.shape):
+            raise ValueError("fit_gh: err must have the shape of the profiles")
+    gh = torch.empty((deg_gh + 1,) + lead, dtype=torch.float64, device=dev)
+    best = torch.empty(lead + (nv,), dtype=torch.float64, device=dev) if want_bestfit else None
+    status = torch.empty(lead, dtype=torch.int32, device=dev)
+    niter = torch.empty(lead, dtype=torch.int32, device=dev)
+    chi2 = torch.empty(lead, dtype=torch.float64, device=dev)
+    _lib.call("pnm_fit_gh", ptr(profiles), ptr(err) if err is not None else None, nspax, nv, ptr(bv), int(deg_gh),
+              lo_v, hi_v, lo_s, hi_s, 0.2, 0.02, lo_s, float(ftol), float(xtol), float(gtol), int(maxiter),
+              ptr(gh), ptr(best) if best is not None else None, ptr(status), ptr(niter), ptr(chi2), stream_ptr())
+    return gh, best, status, niter, chi2
+
+
 def rotate_soa(soa3, mat, out=None):
     """pnm_rotate on three SoA tensors -> three new tensors (rows of a (3, N) tensor)."""
     x, y, z = soa3

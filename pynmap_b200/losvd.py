@@ -61,6 +61,29 @@ class LOSVD(object):
         m0, m1, m2 = engine.cube_moments(cube, _np(self.binv))
         self.mom0, self.mom1, self.mom2 = (engine.to_output(m, want_torch) for m in (m0, m1, m2))
 
+    # ------------------------------------------------------------------ f4: Gauss-Hermite fit
+    def fitlosvd(self, degree=4, on_error="raise", **kwargs):
+        """Fit every LOSVD with a Gauss-Hermite series (pynmap/losvd.py:53-67 looping
+        fit_losvd.fitgh): all spaxels in one kernel.  Sets ``GH`` (degree + 1, nx, ny) = I, V, S,
+        h3.., ``bestfit`` (nx, ny, nv) and ``resfit`` (per-spaxel status / niter / fnorm).  The
+        reference allocates ``GH`` with 5 rows, i.e. only degree=4 works there.
+
+        A spaxel whose start values fall outside the limits (e.g. a single occupied channel:
+        sigma = 0) makes the reference raise from mpfit; ``on_error="flag"`` marks such spaxels
+        with status 0 and NaN parameters instead."""
+        from . import fit_losvd
+        cube, want_torch = self._cube_on_device(self.losvd)
+        err = None
+        if self._has_errors():
+            err, _ = self._cube_on_device(self.err_losvd)
+        gh, best, status, niter, chi2 = fit_losvd.fit_profiles(_np(self.binv), cube, deg_gh=degree, err=err, **kwargs)
+        status_h = status.cpu().numpy()
+        if on_error == "raise" and np.any(status_h == 0):
+            raise Exception(fit_losvd.OUTSIDE_LIMITS_MSG)
+        self.GH = engine.to_output(gh, want_torch)
+        self.bestfit = engine.to_output(best, want_torch)
+        self.resfit = fit_losvd.FitResults(gh.cpu().numpy(), status_h, niter.cpu().numpy(), chi2.cpu().numpy())
+
     # ------------------------------------------------------------------ f3: spatial rebin
     def rebin_spatial(self, factorx=1, factory=1, function='sum'):
         """Rebin by integer factors in X and Y (pynmap/losvd.py:69-92 with misc_io.rebin_1darray /
