@@ -197,10 +197,14 @@ int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv,
  * For each of the nspax profiles cube[s][0..nv) minimise sum(((d - A u(p)) / err)^2) over
  * p = (V, S, h3 .. h_deg_gh) with A = sum((d/err)^2) / sum((d/err)(u/err)) re-solved at every
  * evaluation (fit_losvd.py:25-54, :178-185), u = gausshermite(binv, [1, p]) (misc_functions.py:
- * 15-68); start at the profile's moments with h_n = guess_h; box limits [lo_v, hi_v], [lo_s, hi_s],
- * +-lim_h (fit_losvd.py:157-165).  Bounded Levenberg-Marquardt with an analytic Jacobian; the limits
- * are handled and the convergence tests (ftol, xtol, gtol, maxiter) and status codes defined as in
- * utils/mpfit.py:1074-1094, :1171-1230, :1303-1322.  err_dev may be NULL (unit errors).
+ * 15-68).  Bounded Levenberg-Marquardt with an analytic Jacobian; limits, convergence tests (ftol,
+ * xtol, gtol, maxiter) and status codes as in utils/mpfit.py:1074-1094, :1171-1230, :1303-1322.
+ * HOST arrays of deg_gh entries (the parinfo of fit_losvd.py:203-205):
+ *   start  start value, NaN = the reference's default: the profile's moments for V and S
+ *          (fit_losvd.py:138, :158), guess_h for h_n; may be NULL (all defaults)
+ *   lo, hi limits, -inf / +inf where not limited
+ *   fixed  non-zero = held at its start value; may be NULL
+ * err_dev may be NULL (unit errors).  empty_m2 = min(diff(binv)) / 3 (moment012 of an empty profile).
  *   gh      [deg_gh + 1][nspax]  (I, V, S, h3 ..)      bestfit [nspax][nv] or NULL
  *   status  [nspax]  1..4 converged, 5 maxiter, -16 non-finite (e.g. all-zero profile: I = NaN and
  *                    p = start values, as the reference returns), 0 start values outside the limits
@@ -208,7 +212,7 @@ int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv,
  *   niter   [nspax]  accepted steps + 1 (mpfit's niter)       chi2 [nspax] final sum of squares
  * deg_gh in 2..6.                                                                                */
 int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t nv, const double* binv_dev,
-               int32_t deg_gh, double lo_v, double hi_v, double lo_s, double hi_s, double lim_h,
+               int32_t deg_gh, const double* start, const double* lo, const double* hi, const int32_t* fixed,
                double guess_h, double empty_m2, double ftol, double xtol, double gtol, int32_t maxiter,
                double* gh, double* bestfit, int32_t* status, int32_t* niter, double* chi2, void* stream);
 

@@ -223,6 +223,25 @@ def make_fit_golden(ref, save):
     gh, status, niter, fnorm, best = run(prof, 4, errs)
     out.update(data_err=prof, err=errs, gh_err=gh, status_err=status, niter_err=niter, fnorm_err=fnorm, best_err=best)
 
+    # non-default parinfo (fit_losvd.py:166-176): partial start values, a fixed parameter, unlimited h_n, tight limits
+    truth = np.stack([rng.uniform(20.0, 200.0, 12), rng.uniform(-90.0, 90.0, 12), rng.uniform(40.0, 110.0, 12),
+                      rng.uniform(-0.15, 0.15, 12), rng.uniform(-0.15, 0.15, 12)], 1)
+    prof = np.stack([rng.poisson(np.maximum(mf.gausshermite(x, t), 0.0)).astype(np.float64) for t in truth])
+    out["data_custom"] = prof
+    custom = {"A": dict(params=[10.0, 80.0]),
+              "B": dict(fixed=[False, False, True, False]),
+              "C": dict(limitedmin=[True, True, False, False], limitedmax=[True, True, False, False]),
+              "D": dict(minpars=[-100.0, 30.0, -0.05, -0.05], maxpars=[100.0, 120.0, 0.05, 0.05], params=[0.0, 60.0, 0.0, 0.0])}
+    for tag, kw in custom.items():
+        gh = np.zeros((len(prof), 5))
+        fn = np.zeros(len(prof))
+        for i, d in enumerate(prof):
+            with np.errstate(all="ignore"):
+                gh[i], res, _ = quiet(fl.fitgh, x, d, deg_gh=4, verbose=False, **kw)
+            fn[i] = res.fnorm
+        out["gh_custom" + tag] = gh
+        out["fnorm_custom" + tag] = fn
+
     # LOSVD.fitlosvd on a populated cube
     pos, vel, mass = toy_snapshot(60000, 5, np.float64)
     lim = [-3.0, 3.0, -3.0, 3.0]

@@ -425,20 +425,37 @@ int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv, con
 }
 
 int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t nv, const double* binv_dev,
-               int32_t deg_gh, double lo_v, double hi_v, double lo_s, double hi_s, double lim_h, double guess_h,
-               double empty_m2, double ftol, double xtol, double gtol, int32_t maxiter, double* gh, double* bestfit,
-               int32_t* status, int32_t* niter, double* chi2, void* stream) {
-    if (nspax < 0 || nv < 1 || maxiter < 0) return fail(PNM_EINVAL, "pnm_fit_gh: bad sizes");
-    if (deg_gh < 2 || deg_gh > 6) return fail(PNM_ELIMIT, "pnm_fit_gh: deg_gh must be in 2..6 (got %d)", deg_gh);
-    if (nv <= deg_gh) return fail(PNM_EINVAL, "pnm_fit_gh: number of parameters must not exceed data");
+               int32_t deg_gh, const double* start, const double* lo, const double* hi, const int32_t* fixed,
+               double guess_h, double empty_m2, double ftol, double xtol, double gtol, int32_t maxiter, double* gh,
+               double* bestfit, int32_t* status, int32_t* niter, double* chi2, void* stream) {
+    if (nspax < 0 || nv < 1) return fail(PNM_EINVAL, "pnm_fit_gh: bad sizes");
+    if (deg_gh < 2 || deg_gh > pnm::kFitMaxPar)
+        return fail(PNM_ELIMIT, "pnm_fit_gh: deg_gh must be in 2..%d (got %d)", pnm::kFitMaxPar, deg_gh);
+    if (!lo || !hi) return fail(PNM_EINVAL, "pnm_fit_gh: null limits");
+    if (!(ftol > 0.0) || !(xtol > 0.0) || !(gtol > 0.0) || maxiter < 0)
+        return fail(PNM_EINVAL, "pnm_fit_gh: input keywords are inconsistent");            // mpfit.py:985-988
+    int nfree = 0;
+    for (int k = 0; k < deg_gh; ++k) {
+        const bool fx = fixed && fixed[k];
+        nfree += fx ? 0 : 1;
+        if (lo[k] != lo[k] || hi[k] != hi[k] || (!fx && std::isfinite(lo[k]) && std::isfinite(hi[k]) && lo[k] >= hi[k]))
+            return fail(PNM_EINVAL, "pnm_fit_gh: parameter limits are not consistent");      // mpfit.py:959-963
+    }
+    if (nfree == 0) return fail(PNM_EINVAL, "pnm_fit_gh: no free parameters");               // mpfit.py:942-944
+    if (nv < nfree) return fail(PNM_EINVAL, "pnm_fit_gh: number of parameters must not exceed data");   // mpfit.py:1016-1018
     if (nspax == 0) return PNM_OK;
     if (!cube || !binv_dev || !gh || !status || !niter || !chi2) return fail(PNM_EINVAL, "pnm_fit_gh: null argument");
-    if (!(lo_v <= hi_v) || !(lo_s <= hi_s) || !(lo_s > 0.0) || !(lim_h >= 0.0))
-        return fail(PNM_EINVAL, "pnm_fit_gh: parameter limits are not consistent");
     pnm::FitParams P;
     P.cube = cube; P.err = err_dev; P.binv = binv_dev; P.nv = nv; P.nspax = nspax;
-    P.lo_v = lo_v; P.hi_v = hi_v; P.lo_s = lo_s; P.hi_s = hi_s; P.lim_h = lim_h; P.guess_h = guess_h;
-    P.empty_m2 = empty_m2; P.ftol = ftol; P.xtol = xtol; P.gtol = gtol; P.maxiter = maxiter;
+    P.fixed_mask = 0;
+    for (int k = 0; k < pnm::kFitMaxPar; ++k) {
+        const bool used = k < deg_gh;
+        P.start[k] = (used && start) ? start[k] : std::nan("");
+        P.lo[k] = used ? lo[k] : 0.0;
+        P.hi[k] = used ? hi[k] : 0.0;
+        if (used && fixed && fixed[k]) P.fixed_mask |= 1u << k;
+    }
+    P.guess_h = guess_h; P.empty_m2 = empty_m2; P.ftol = ftol; P.xtol = xtol; P.gtol = gtol; P.maxiter = maxiter;
     P.gh = gh; P.bestfit = bestfit; P.status = status; P.niter = niter; P.chi2 = chi2;
     const unsigned grid = (unsigned)((nspax + pnm::kFitWarps - 1) / pnm::kFitWarps);
     const int threads = pnm::kFitWarps * 32;

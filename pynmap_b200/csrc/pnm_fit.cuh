@@ -18,14 +18,19 @@
 
 namespace pnm {
 
+constexpr int kFitMaxPar = 6;
+
 struct FitParams {
     const double* cube;     // [nspax][nv]
     const double* err;      // [nspax][nv] or null (fit_losvd.py:180-185)
     const double* binv;     // [nv]
     int32_t nv;
     int64_t nspax;
-    double lo_v, hi_v, lo_s, hi_s;   // limits of V and S (fit_losvd.py:160-163)
-    double lim_h, guess_h;           // +-0.2 and 0.02 (fit_losvd.py:157-162)
+    double start[kFitMaxPar];        // NaN: the default (moments for V, S; guess_h for h_n) -- fit_losvd.py:157-158, :169
+    double lo[kFitMaxPar];           // -inf / +inf when not limited (fit_losvd.py:159-165, :170-174)
+    double hi[kFitMaxPar];
+    uint32_t fixed_mask;             // bit k: parameter k is held at its start value (fit_losvd.py:166, :170)
+    double guess_h;                  // 0.02 (fit_losvd.py:157)
     double empty_m2;                 // min(diff(binv)) / 3 (misc_functions.py:84)
     double ftol, xtol, gtol;
     int32_t maxiter;
@@ -234,9 +239,12 @@ __global__ void __launch_bounds__(kFitWarps * 32) k_fit_gh(const FitParams P) {
     m0 = warp_sum(m0); mx = warp_sum(mx); mxx = warp_sum(mxx); d2 = warp_sum(d2);
 
     double p[NP], lo[NP], hi[NP];
+    bool fixed[NP];
 #pragma unroll
-    for (int k = 0; k < NP; ++k) { p[k] = P.guess_h; lo[k] = -P.lim_h; hi[k] = P.lim_h; }
-    lo[0] = P.lo_v; hi[0] = P.hi_v; lo[1] = P.lo_s; hi[1] = P.hi_s;
+    for (int k = 0; k < NP; ++k) {
+        p[k] = P.guess_h; lo[k] = P.lo[k]; hi[k] = P.hi[k];
+        fixed[k] = (P.fixed_mask >> k) & 1u;
+    }
     if (any) {
         p[0] = mx / m0;
         p[1] = sqrt(mxx / m0 - p[0] * p[0]);
@@ -244,6 +252,9 @@ __global__ void __launch_bounds__(kFitWarps * 32) k_fit_gh(const FitParams P) {
         p[0] = 0.0;
         p[1] = P.empty_m2;
     }
+#pragma unroll
+    for (int k = 0; k < NP; ++k)
+        if (P.start[k] == P.start[k]) p[k] = P.start[k];
 
     int status = 0, niter = 1;
     double amp = 0.0, f = 0.0;
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(kFitWarps * 32) k_fit_gh(const FitParams P) {
             const double fnorm = sqrt(st.f);
 #pragma unroll
             for (int k = 0; k < NP; ++k) {
-                peg[k] = (p[k] == lo[k] && st.g[k] > 0.0) || (p[k] == hi[k] && st.g[k] < 0.0);
+                peg[k] = fixed[k] || (p[k] == lo[k] && st.g[k] > 0.0) || (p[k] == hi[k] && st.g[k] < 0.0);
                 const double hd = sqrt(st.h[k][k]);
                 if (!peg[k] && hd > 0.0 && st.f > 0.0) gnorm = fmax(gnorm, fabs(st.g[k]) / (hd * fnorm));
                 diag[k] = fmax(diag[k], hd > 0.0 ? hd : 1.0);
@@ -319,8 +330,10 @@ __global__ void __launch_bounds__(kFitWarps * 32) k_fit_gh(const FitParams P) {
                     const double sgu = hi[k] >= 0.0 ? 1.0 : -1.0, sgl = lo[k] >= 0.0 ? 1.0 : -1.0;
                     if (pn[k] >= hi[k] * (1.0 - sgu * eps) - (hi[k] == 0.0 ? eps : 0.0)) pn[k] = hi[k];   // mpfit.py:1218-1230
                     if (pn[k] <= lo[k] * (1.0 + sgl * eps) + (lo[k] == 0.0 ? eps : 0.0)) pn[k] = lo[k];
-                    pnorm += diag[k] * s[k] * diag[k] * s[k];
-                    xnorm += diag[k] * p[k] * diag[k] * p[k];
+                    if (!fixed[k]) {                    // mpfit's norms run over the free parameters
+                        pnorm += diag[k] * s[k] * diag[k] * s[k];
+                        xnorm += diag[k] * p[k] * diag[k] * p[k];
+                    }
                     gs += st.g[k] * s[k];
                 }
 #pragma unroll
@@ -346,7 +359,8 @@ __global__ void __launch_bounds__(kFitWarps * 32) k_fit_gh(const FitParams P) {
                     fit_eval<NP>(P, d, er, lane, p, d2, st);
                     xnorm = 0.0;
 #pragma unroll
-                    for (int k = 0; k < NP; ++k) xnorm += diag[k] * p[k] * diag[k] * p[k];
+                    for (int k = 0; k < NP; ++k)
+                        if (!fixed[k]) xnorm += diag[k] * p[k] * diag[k] * p[k];
                     xnorm = sqrt(xnorm);
                 } else {
                     lam *= nu; nu *= 2.0;

@@ -391,11 +391,24 @@ def cube_moments(cube, binv):
     return m0, m1, m2
 
 
-def fit_gh(profiles, binv, deg_gh=4, err=None, ftol=1e-10, xtol=1e-10, gtol=1e-10, maxiter=200,
-           want_bestfit=True):
+def fit_gh_defaults(binv, deg_gh):
+    """Start values (NaN = from the profile's moments), lower and upper limits of fit_losvd.py:157-163."""
+    binv = np.asarray(binv, dtype=np.float64).ravel()
+    start = np.full(deg_gh, 0.02)
+    start[:2] = np.nan
+    lo = np.full(deg_gh, -0.2)
+    lo[:2] = (np.min(binv), np.min(np.diff(binv)) / 3.0)
+    hi = np.full(deg_gh, 0.2)
+    hi[:2] = (np.max(binv), (np.max(binv) - np.min(binv)) / 3.0)
+    return start, lo, hi
+
+
+def fit_gh(profiles, binv, deg_gh=4, err=None, start=None, lo=None, hi=None, fixed=None,
+           ftol=1e-10, xtol=1e-10, gtol=1e-10, maxiter=200, want_bestfit=True):
     """pnm_fit_gh on ``profiles`` (..., nv): Gauss-Hermite fit of every profile (row f4;
-    fit_losvd.py:84-235 with its default limits and start values, :157-165).  Returns
-    (gh (deg_gh+1, ...), bestfit (..., nv) or None, status, niter, chi2) as device tensors."""
+    fit_losvd.py:84-235).  ``start`` / ``lo`` / ``hi`` / ``fixed`` are per-parameter arrays of
+    deg_gh entries (defaults: fit_gh_defaults, nothing fixed).  Returns (gh (deg_gh+1, ...),
+    bestfit (..., nv) or None, status, niter, chi2) as device tensors."""
     profiles = profiles.contiguous()
     lead, nv = tuple(profiles.shape[:-1]), int(profiles.shape[-1])
     nspax = int(np.prod(lead)) if lead else 1
@@ -404,9 +417,16 @@ def fit_gh(profiles, binv, deg_gh=4, err=None, ftol=1e-10, xtol=1e-10, gtol=1e-1
         raise ValueError("fit_gh: the velocity axis has {} points, the profiles {}".format(binv.size, nv))
     dev = profiles.device
     bv = to_device(binv, torch.float64, dev)
-    dx = np.diff(binv)
-    lo_v, hi_v = float(np.min(binv)), float(np.max(binv))                 # fit_losvd.py:160-163
-    lo_s, hi_s = float(np.min(dx) / 3.0), float((hi_v - lo_v) / 3.0)
+    d_start, d_lo, d_hi = fit_gh_defaults(binv, deg_gh)
+    arrs = []
+    for given, default in ((start, d_start), (lo, d_lo), (hi, d_hi)):
+        a = np.ascontiguousarray(default if given is None else given, dtype=np.float64)
+        if a.shape != (deg_gh,):
+            raise ValueError("fit_gh: per-parameter arrays need deg_gh = {} entries".format(deg_gh))
+        arrs.append(a)
+    fx = np.ascontiguousarray(np.zeros(deg_gh) if fixed is None else fixed).astype(np.int32)
+    if fx.shape != (deg_gh,):
+        raise ValueError("fit_gh: per-parameter arrays need deg_gh = {} entries".format(deg_gh))
     if err is not None:
         err = err.contiguous()
         if tuple(err.shape) != tuple(profiles.shape):
@@ -416,8 +436,10 @@ def fit_gh(profiles, binv, deg_gh=4, err=None, ftol=1e-10, xtol=1e-10, gtol=1e-1
     status = torch.empty(lead, dtype=torch.int32, device=dev)
     niter = torch.empty(lead, dtype=torch.int32, device=dev)
     chi2 = torch.empty(lead, dtype=torch.float64, device=dev)
+    dptr = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
     _lib.call("pnm_fit_gh", ptr(profiles), ptr(err) if err is not None else None, nspax, nv, ptr(bv), int(deg_gh),
-              lo_v, hi_v, lo_s, hi_s, 0.2, 0.02, lo_s, float(ftol), float(xtol), float(gtol), int(maxiter),
+              dptr(arrs[0]), dptr(arrs[1]), dptr(arrs[2]), fx.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+              0.02, float(np.min(np.diff(binv)) / 3.0), float(ftol), float(xtol), float(gtol), int(maxiter),
               ptr(gh), ptr(best) if best is not None else None, ptr(status), ptr(niter), ptr(chi2), stream_ptr())
     return gh, best, status, niter, chi2
 

@@ -52,7 +52,24 @@ class FitResults(object):
         return (self[i] for i in range(len(self)))
 
 
-_UNSUPPORTED = ("params", "fixed", "limitedmin", "limitedmax", "minpars", "maxpars")
+def _set_ghparameters(parlist, default, deg_gh):
+    """fit_losvd.py:414-439: a short list is completed with the defaults."""
+    if parlist is None:
+        parlist = default
+    parlist = list(parlist)[:deg_gh]
+    return parlist + list(default[len(parlist):])
+
+
+def _parinfo(xax, deg_gh, params=None, fixed=None, limitedmin=None, limitedmax=None, minpars=None, maxpars=None):
+    """The per-parameter start / limits / fixed arrays of fit_losvd.py:157-176 and :203-205."""
+    d_start, d_lo, d_hi = engine.fit_gh_defaults(xax, deg_gh)
+    start = np.asarray(_set_ghparameters(params, d_start, deg_gh), dtype=np.float64)
+    fixed = np.asarray(_set_ghparameters(fixed, [False] * deg_gh, deg_gh), dtype=bool)
+    limitedmin = np.asarray(_set_ghparameters(limitedmin, [True] * deg_gh, deg_gh), dtype=bool)
+    limitedmax = np.asarray(_set_ghparameters(limitedmax, [True] * deg_gh, deg_gh), dtype=bool)
+    lo = np.where(limitedmin, np.asarray(_set_ghparameters(minpars, d_lo, deg_gh), dtype=np.float64), -np.inf)
+    hi = np.where(limitedmax, np.asarray(_set_ghparameters(maxpars, d_hi, deg_gh), dtype=np.float64), np.inf)
+    return dict(start=start, lo=lo, hi=hi, fixed=fixed)
 
 
 def _fit_options(kwargs):
@@ -65,10 +82,12 @@ def _fit_options(kwargs):
     return opts
 
 
-def fit_profiles(xax, profiles, deg_gh=4, err=None, want_bestfit=True, **kwargs):
-    """Fit all profiles (..., nv) at once; tensors stay on the device.  Returns
-    (gh (deg_gh + 1, ...), bestfit, status, niter, chi2)."""
+def fit_profiles(xax, profiles, deg_gh=4, err=None, want_bestfit=True, params=None, fixed=None,
+                 limitedmin=None, limitedmax=None, minpars=None, maxpars=None, **kwargs):
+    """Fit all profiles (..., nv) at once with one set of start values / limits (fitgh's keywords);
+    tensors stay on the device.  Returns (gh (deg_gh + 1, ...), bestfit, status, niter, chi2)."""
     opts = _fit_options(kwargs)
+    opts.update(_parinfo(xax, deg_gh, params, fixed, limitedmin, limitedmax, minpars, maxpars))
     dev = engine.current_device()
     if not isinstance(profiles, torch.Tensor):
         profiles = torch.from_numpy(np.ascontiguousarray(profiles, dtype=np.float64))
@@ -88,19 +107,22 @@ def fitgh(xax, data, deg_gh=2, err=None, params=None, fixed=None, limitedmin=Non
     if optimiser != "mpfit":
         print("ERROR: optimiser must be lmfit or mpfit")      # lmfit is not available on this path
         return None, None, None
-    given = dict(params=params, fixed=fixed, limitedmin=limitedmin, limitedmax=limitedmax,
-                 minpars=minpars, maxpars=maxpars)
-    custom = [k for k in _UNSUPPORTED if given[k] is not None]
-    if custom:
-        raise NotImplementedError("fitgh: only the default start values and limits "
-                                  "(fit_losvd.py:157-165) are implemented; got {}".format(custom))
+    if isinstance(params, np.ndarray):
+        params = params.tolist()
+    if params is not None and len(params) > deg_gh:           # fit_losvd.py:140-146
+        print("ERROR: input parameter array (params) is "
+              "larger than expected")
+        print("ERROR: It is %d while it should be smaller or "
+              "equal to %s (deg_gh)", len(params), deg_gh)
+        return 0., 0., 0., 0.
     data = np.asarray(data, dtype=np.float64)
     if xax is None:
         xax = np.arange(len(data))
     xax = np.asarray(xax, dtype=np.float64).ravel()
     gh, best, status, niter, chi2 = fit_profiles(xax, data.reshape(1, -1), deg_gh=deg_gh,
                                                  err=None if err is None else np.asarray(err).reshape(1, -1),
-                                                 **kwargs)
+                                                 params=params, fixed=fixed, limitedmin=limitedmin,
+                                                 limitedmax=limitedmax, minpars=minpars, maxpars=maxpars, **kwargs)
     gh = gh.cpu().numpy()[:, 0]
     result = FitResult(gh[1:].copy(), status.item(), niter.item(), chi2.item())
     if result.status == 0:

@@ -95,6 +95,28 @@ def test_gpu_fit_with_errors(golden):
 
 
 @pytest.mark.gpu
+def test_gpu_fit_with_user_parinfo(golden):
+    """Partial start values, a fixed parameter, unlimited h_n, tight limits (fit_losvd.py:166-176)."""
+    from pynmap_b200 import fit_losvd
+    g = golden("fit")
+    x, data = g["x"], g["data_custom"]
+    custom = {"A": dict(params=[10.0, 80.0]),
+              "B": dict(fixed=[False, False, True, False]),
+              "C": dict(limitedmin=[True, True, False, False], limitedmax=[True, True, False, False]),
+              "D": dict(minpars=[-100.0, 30.0, -0.05, -0.05], maxpars=[100.0, 120.0, 0.05, 0.05],
+                        params=[0.0, 60.0, 0.0, 0.0])}
+    for tag, kw in custom.items():
+        gh, best, status, niter, chi2 = fit_losvd.fit_profiles(x, data, deg_gh=4, **kw)
+        gh = gh.cpu().numpy().T
+        diff = scaled_diff(gh, g["gh_custom" + tag])
+        assert diff.max() < TOL, (tag, diff.max())
+        assert (chi2.cpu().numpy() <= g["fnorm_custom" + tag] * (1 + 1e-9)).all()
+    assert (gh[:, 3:] >= -0.05).all() and (gh[:, 3:] <= 0.05).all() and (np.abs(gh[:, 3:]) == 0.05).any()
+    one = fit_losvd.fitgh(x, data[2], deg_gh=4, verbose=False, **custom["B"])
+    assert one[0][3] == 0.02 and scaled_diff(one[0][None], g["gh_customB"][2:3]).max() < TOL
+
+
+@pytest.mark.gpu
 def test_gpu_fitlosvd_on_cube(golden):
     import torch
     from pynmap_b200 import LOSVD
@@ -137,8 +159,12 @@ def test_gpu_fitgh_single_profile_and_errors(golden, capsys):
         lv.fitlosvd(degree=4)
     lv.fitlosvd(degree=4, on_error="flag")
     assert lv.resfit[1].status == 0 and np.isnan(lv.GH[:, 0, 1]).all() and np.isfinite(lv.GH[:, 0, 0]).all()
-    with pytest.raises(NotImplementedError):
-        fit_losvd.fitgh(x, g["data4"][0], deg_gh=4, params=[0.0, 50.0, 0.0, 0.0])
+    out = fit_losvd.fitgh(x, g["data4"][0], deg_gh=4, params=[0.0, 50.0, 0.0, 0.0, 0.0], verbose=False)
+    assert out == (0., 0., 0., 0.) and "larger than expected" in capsys.readouterr().out     # fit_losvd.py:140-146
+    with pytest.raises(Exception, match="no free parameters"):
+        fit_losvd.fitgh(x, g["data4"][0], deg_gh=2, params=[0.0, 50.0], fixed=[True, True], verbose=False)
+    with pytest.raises(Exception, match="limits are not consistent"):
+        fit_losvd.fitgh(x, g["data4"][0], deg_gh=2, minpars=[50.0, 10.0], maxpars=[-50.0, 100.0], verbose=False)
     with pytest.raises(Exception):
         fit_losvd.fit_profiles(x, g["data4"], deg_gh=7)                  # outside the compiled range, loud
 
