@@ -212,6 +212,9 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)   # the reduce must not queue behind the scatter
+        if args.nccl_max_ctas > 0:               # fewer reduce CTAs = fewer SMs taken from the scatter kernel
+            opts.config.max_ctas = args.nccl_max_ctas
+            opts.config.min_ctas = min(opts.config.min_ctas, args.nccl_max_ctas) if opts.config.min_ctas > 0 else 1
         dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 
     import pynmap_b200 as pnm
@@ -396,6 +399,8 @@ def main():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="run post-processing on the scatter stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nccl-max-ctas", type=int, default=4,
+                    help="cap on the CTAs of the NCCL reduce, which shares the SMs with the scatter kernel (0 = NCCL's choice)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
