@@ -257,6 +257,11 @@ def run_b200(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # setup, not warm-up: NCCL builds its connections lazily per reduce root, so every owner rank is
+    # used once before the W warm-up steps (otherwise a short W leaves connection setup in the timed region)
+    for _ in range(world if reducer is not None else 0):
+        step()
+    fence()
     for _ in range(max(3, args.warmup)):
         step()
     fence()
