@@ -68,6 +68,9 @@ extern "C" {
  * directly: particles inside the V range go to the cube only, the others to maps slot 0,
  * and pnm_finalize_vmaps adds the cube's V-sum back.  One atomic fewer per particle.       */
 #define PNM_W_FROM_CUBE 16
+/* pnm_finalize_vmaps only: the first map replica already holds the totals (pnm_fold_maps, possibly
+ * followed by a reduction over ranks); the other replicas are not read.                          */
+#define PNM_MAPS_FOLDED 32
 
 /* mask semantics of the reference */
 #define PNM_MASK_NONE 0
@@ -109,9 +112,12 @@ int pnm_grid_destroy(pnm_grid* g);
 int64_t pnm_maps_acc_elems(const pnm_grid* g); /* replicas*ny*nx*PNM_MAP_SLOTS */
 int64_t pnm_cube_acc_elems(const pnm_grid* g); /* nx*ny*nv                     */
 int pnm_grid_map_replicas(const pnm_grid* g);
-/* Sums the map replicas into the first one (and clears the rest), so that a multi-GPU reduction
- * only has to move the first ny*nx*PNM_MAP_SLOTS elements.                                      */
-int pnm_fold_maps(const pnm_grid* g, void* acc_maps, int acc_mode, void* stream);
+/* Sums the map replicas into the first one, so that a multi-GPU reduction only has to move the
+ * first ny*nx*PNM_MAP_SLOTS elements.  clear_others != 0 also zeroes replicas 1.. (the buffer can
+ * then keep accumulating); with 0 they are left as they are and the buffer must be finalised with
+ * PNM_MAPS_FOLDED in `sums` (half the memory traffic: the fold runs next to the following step's
+ * scatter in the sharded pipeline).                                                              */
+int pnm_fold_maps(const pnm_grid* g, void* acc_maps, int acc_mode, int clear_others, void* stream);
 
 /* ---- fused rotate + project + bin (a1+a2+a3+a4) ---------------------------------------------
  * For each of `nviews` views: apply `nchain` float32 matrices in sequence to (x,y,z) and

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("PNM_B200_LIB", os.path.join(_HERE, "libpnm_b200.so"))
 # constants mirrored from include/pnm_b200.h
 F32, F64 = 0, 1
 ACC_F64, ACC_FIXED = 0, 1
-SUM_W, SUM_WD, SUM_WD2, SUM_CUBE, W_FROM_CUBE = 1, 2, 4, 8, 16
+SUM_W, SUM_WD, SUM_WD2, SUM_CUBE, W_FROM_CUBE, MAPS_FOLDED = 1, 2, 4, 8, 16, 32
 MASK_NONE, MASK_AND_NONFINITE, MASK_PLAIN = 0, 1, 2
 MAX_EDGES, MAX_CHAIN, MAX_VIEWS, MAX_TAPS, MAP_SLOTS = 4097, 8, 64, 255, 4
 MAX_MATS = 64
@@ -31,7 +31,7 @@ _SIGNATURES = {
     "pnm_maps_acc_elems": (c_int64, [_P]),
     "pnm_cube_acc_elems": (c_int64, [_P]),
     "pnm_grid_map_replicas": (c_int, [_P]),
-    "pnm_fold_maps": (c_int, [_P, _P, c_int, _P]),
+    "pnm_fold_maps": (c_int, [_P, _P, c_int, c_int, _P]),
     "pnm_project_bin": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_int,
                                 POINTER(c_float), c_int, c_int, c_int, c_int, POINTER(c_double), _P, _P, _P]),
     "pnm_bin_points": (c_int, [_P, c_int64, c_int, _P, _P, _P, _P, _P, c_int, c_int, c_int,

@@ -331,13 +331,14 @@ int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_
     const int npix = g->nx * g->ny;
     const int grid = (npix + 31) / 32;
     const dim3 block(32, 8);
+    const int replicas = (sums & PNM_MAPS_FOLDED) ? 1 : g->replicas;
     if (acc_mode == PNM_ACC_F64) {
         pnm::k_finalize_vmaps<PNM_ACC_F64><<<grid, block, 0, as_stream(stream)>>>(acc_maps, acc_cube, g->nx, g->ny, g->nv,
-                                                                              g->replicas, wfc, 1.0, 1.0, 1.0, M, V, S, S1, S2);
+                                                                              replicas, wfc, 1.0, 1.0, 1.0, M, V, S, S1, S2);
     } else if (acc_mode == PNM_ACC_FIXED) {
         if (!scales3_host) return fail(PNM_EINVAL, "pnm_finalize_vmaps: FIXED mode needs scales");
         pnm::k_finalize_vmaps<PNM_ACC_FIXED><<<grid, block, 0, as_stream(stream)>>>(
-            acc_maps, acc_cube, g->nx, g->ny, g->nv, g->replicas, wfc, 1.0 / scales3_host[0], 1.0 / scales3_host[1],
+            acc_maps, acc_cube, g->nx, g->ny, g->nv, replicas, wfc, 1.0 / scales3_host[0], 1.0 / scales3_host[1],
             1.0 / scales3_host[2], M, V, S, S1, S2);
     } else {
         return fail(PNM_EINVAL, "pnm_finalize_vmaps: acc_mode %d", acc_mode);
@@ -381,13 +382,19 @@ int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int acc_mode, dou
     return PNM_OK;
 }
 
-int pnm_fold_maps(const pnm_grid* g, void* acc_maps, int acc_mode, void* stream) {
+int pnm_fold_maps(const pnm_grid* g, void* acc_maps, int acc_mode, int clear_others, void* stream) {
     if (!g || !acc_maps) return fail(PNM_EINVAL, "pnm_fold_maps: null argument");
+    if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_fold_maps: acc_mode %d", acc_mode);
     const int64_t per = (int64_t)g->nx * g->ny * PNM_MAP_SLOTS;
     const int grid = (int)((per + 255) / 256);
-    if (acc_mode == PNM_ACC_F64) pnm::k_fold_maps<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, per, g->replicas);
-    else if (acc_mode == PNM_ACC_FIXED) pnm::k_fold_maps<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(acc_maps, per, g->replicas);
-    else return fail(PNM_EINVAL, "pnm_fold_maps: acc_mode %d", acc_mode);
+    cudaStream_t s = as_stream(stream);
+    if (acc_mode == PNM_ACC_F64) {
+        if (clear_others) pnm::k_fold_maps<PNM_ACC_F64, true><<<grid, 256, 0, s>>>(acc_maps, per, g->replicas);
+        else pnm::k_fold_maps<PNM_ACC_F64, false><<<grid, 256, 0, s>>>(acc_maps, per, g->replicas);
+    } else {
+        if (clear_others) pnm::k_fold_maps<PNM_ACC_FIXED, true><<<grid, 256, 0, s>>>(acc_maps, per, g->replicas);
+        else pnm::k_fold_maps<PNM_ACC_FIXED, false><<<grid, 256, 0, s>>>(acc_maps, per, g->replicas);
+    }
     PNM_CUDA(cudaGetLastError());
     return PNM_OK;
 }

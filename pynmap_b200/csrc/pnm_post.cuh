@@ -103,22 +103,27 @@ __global__ void __launch_bounds__(256) k_finalize_map(const void* acc_maps, int 
     if (DW) DW[pix] = s1;
 }
 
-// fold the map replicas into replica 0 (and clear the others) before a multi-GPU reduce
-template <int ACC>
+// fold the map replicas into replica 0 (and, if CLEAR, zero the others) before a multi-GPU reduce.
+// Replicas are summed in index order; loads are issued eight at a time.
+template <int ACC, bool CLEAR>
 __global__ void __launch_bounds__(256) k_fold_maps(void* acc_maps, int64_t per_replica, int replicas) {
+    using A = typename AccT<ACC>::type;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= per_replica) return;
-    if (ACC == PNM_ACC_F64) {
-        double* a = reinterpret_cast<double*>(acc_maps);
-        double t = 0.0;
-        for (int r = 0; r < replicas; ++r) { t = __dadd_rn(t, a[r * per_replica + i]); if (r) a[r * per_replica + i] = 0.0; }
-        a[i] = t;
-    } else {
-        long long* a = reinterpret_cast<long long*>(acc_maps);
-        long long t = 0;
-        for (int r = 0; r < replicas; ++r) { t += a[r * per_replica + i]; if (r) a[r * per_replica + i] = 0; }
-        a[i] = t;
+    A* a = reinterpret_cast<A*>(acc_maps) + i;
+    A t = a[0];
+    for (int r = 1; r < replicas; r += 8) {
+        A v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (r + k < replicas) ? a[(int64_t)(r + k) * per_replica] : A(0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            if (ACC == PNM_ACC_F64) t = (A)__dadd_rn((double)t, (double)v[k]);
+            else t += v[k];
+            if (CLEAR && r + k < replicas) a[(int64_t)(r + k) * per_replica] = A(0);
+        }
     }
+    a[0] = t;
 }
 
 // cube accumulator [iv][q] -> reference layout [q][iv] = cube[ix][iy][iv] (grid.py:259) as float64:

@@ -333,10 +333,11 @@ def finalize_cube(grid, cube, acc, scales):
     return out
 
 
-def fold_maps(grid, maps, acc):
+def fold_maps(grid, maps, acc, clear=True):
     """Sum the map replicas into the first one; returns the view that carries the totals (what a
-    multi-GPU reduction has to move)."""
-    _lib.call("pnm_fold_maps", grid.handle, ptr(maps), acc.code, stream_ptr())
+    multi-GPU reduction has to move).  ``clear=False`` leaves the other replicas untouched: cheaper,
+    but the buffer must then be finalised with ``sums | MAPS_FOLDED`` and not accumulated into again."""
+    _lib.call("pnm_fold_maps", grid.handle, ptr(maps), acc.code, 1 if clear else 0, stream_ptr())
     return maps[:grid.maps_fold_elems]
 
 

@@ -467,10 +467,11 @@ class snapshot(object):
     def _project_post(self, grid, maps, cube, sums, acc, scales, reducer):
         """Everything after the scatter of project(): fold + reduce over ranks, finalisation."""
         if reducer is not None:
-            engine.fold_maps(grid, maps, acc)
+            engine.fold_maps(grid, maps, acc, clear=False)     # single-use accumulators: nothing adds to them again
             keep = reducer(*engine.reduce_span(grid, maps, cube))
             if not keep:
                 return None, None
+            sums |= _lib.MAPS_FOLDED
         M, V, S = (self._out(t) for t in engine.finalize_vmaps(grid, maps, cube, sums, acc, scales))
         X, Y = self._mesh(grid)
         newmap = SnapMap(name="Velocity moments", input_dic={"X": X, "Y": Y, "V": V, "M": M, "S": S,

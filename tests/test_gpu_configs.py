@@ -186,7 +186,7 @@ def test_non_uniform_edges_through_the_abi(env):
     P = engine.ptr
     _lib.call("pnm_bin_points", h, n, _lib.F32, P(dev[0]), P(dev[1]), P(dev[2]), P(dev[3]), None, 0, 15, _lib.ACC_FIXED,
               _lib.doubles(scales), P(maps), P(cube), engine.stream_ptr())
-    _lib.call("pnm_fold_maps", h, P(maps), _lib.ACC_FIXED, engine.stream_ptr())
+    _lib.call("pnm_fold_maps", h, P(maps), _lib.ACC_FIXED, 1, engine.stream_ptr())
     out = torch.empty((40, 30, 5), dtype=torch.float64, device="cuda")
     _lib.call("pnm_finalize_cube", h, P(cube), _lib.ACC_FIXED, float(scales[0]), P(out), engine.stream_ptr())
     omaps, ocube = oc.project_bin(pts, w, None, 1, 1, ex, ey, ev, 15, oc.ACC_FIXED, scales, fused=False)

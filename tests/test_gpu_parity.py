@@ -368,6 +368,18 @@ def test_full_size_properties(pnm):
     maps_c, cube_c = run(fx, full, 0, half)
     run(fx, full, half, n, maps_c, cube_c)
     assert torch.equal(fold_a, engine.fold_maps(grid, maps_c, fx)) and torch.equal(cube_a, cube_c)   # linear in the particle set
+    # fold without clearing + PNM_MAPS_FOLDED == finalising all replicas; fold with clearing keeps the buffer summable
+    maps_e = maps_a.clone()
+    fold_e = engine.fold_maps(grid, maps_e, fx, clear=False)
+    assert torch.equal(fold_e, fold_a) and torch.equal(maps_e[grid.maps_fold_elems:], maps_a[grid.maps_fold_elems:])
+    Me = engine.finalize_vmaps(grid, maps_e, cube_a, full | _lib.MAPS_FOLDED, fx, scales)
+    Mref = engine.finalize_vmaps(grid, maps_a, cube_a, full, fx, scales)
+    assert all(torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)) for a, b in zip(Me, Mref))
+    maps_f = maps_a.clone()
+    engine.fold_maps(grid, maps_f, fx)
+    assert grid.map_replicas > 1 and not bool(maps_f[grid.maps_fold_elems:].any())
+    Mf = engine.finalize_vmaps(grid, maps_f, cube_a, full, fx, scales)
+    assert all(torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)) for a, b in zip(Mf, Mref))
     maps_d, cube_d = run(fx, full | 16)                                             # W recovered from the cube
     Ma = engine.finalize_vmaps(grid, maps_a, cube_a, full, fx, scales)
     Md = engine.finalize_vmaps(grid, maps_d, cube_d, full | 16, fx, scales)
