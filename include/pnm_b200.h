@@ -16,6 +16,7 @@
  *   pnm_finalize_cube     weights-histogram -> float64 cube    pynmap/grid.py:259
  *   pnm_smooth_cube       astropy convolve per velocity slice  pynmap/losvd.py:127-135
  *   pnm_cube_moments      moment012 per spaxel                 pynmap/losvd.py:41-51, misc_functions.py:70-90
+ *   pnm_amr_jitter/repeat spread_amr                           pynmap/misc_io.py:184-224
  *   pnm_fit_gh            fitgh (mpfit) per spaxel             pynmap/losvd.py:53-67, fit_losvd.py:57-235
  *   pnm_absmax            (new) bound for the fixed-point scale
  *   pnm_project_host      snapshot.rotate + velocity_moments + create_losvds from HOST arrays
@@ -198,6 +199,16 @@ int pnm_ct_interp(const void* qx, const void* qy, int64_t n, int dtype,
 int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv,
                      const double* binv_dev, double empty_m2,
                      double* mom0, double* mom1, double* mom2, void* stream);
+
+/* ---- f3: spread_amr (misc_io.py:184-224), used by snapshot.amr_velocity_moments (pynmap.py:342-419)
+ * Every AMR cell is replicated nsample times inside its footprint.  The uniform deviates are the
+ * CALLER's (the reference draws them from numpy's global generator, misc_io.py:209; the host layer
+ * does the same, so a seeded run reproduces the reference), scale = box / 2**level per cell.
+ *   pnm_amr_jitter: out[k] = coord[k / nsample] + ((uniform[k] - 0.5) * stretch) * scale[k / nsample], float64
+ *   pnm_amr_repeat: out[k] = values[k / nsample] (/ nsample when divide), in the input dtype        */
+int pnm_amr_jitter(const void* coord, int dtype, const double* scale_dev, const double* uniform_dev, int64_t n,
+                   int32_t nsample, double stretch, double* out, void* stream);
+int pnm_amr_repeat(const void* values, int dtype, int64_t n, int32_t nsample, int divide, void* out, void* stream);
 
 /* ---- f4: Gauss-Hermite fit of every spaxel (losvd.py:53-67, fit_losvd.py:57-235) -------------
  * For each of the nspax profiles cube[s][0..nv) minimise sum(((d - A u(p)) / err)^2) over

@@ -177,6 +177,7 @@ def main():
     save("ssp", age=qa, MH=qm, ML=ML, ML_nofill=ML_nofill, node_age=mData['age'][mw], node_MH=mData['MH'][mw], node_ML=nodes_ml)
 
     make_fit_golden(ref, save)
+    make_amr_golden(ref, save)
 
     for k, v in saved.items():
         print("%-16s %8.1f kB (uncompressed)" % (k, v / 1e3))
@@ -253,6 +254,36 @@ def make_fit_golden(ref, save):
                cube_status=np.array([r.status for r in lv.resfit], dtype=np.int32).reshape(8, 8),
                cube_fnorm=np.array([r.fnorm for r in lv.resfit]).reshape(8, 8))
     save("fit", **out)
+
+
+def make_amr_golden(ref, save):
+    """Row f3, AMR part: misc_io.spread_amr (misc_io.py:184-224) and snapshot.amr_velocity_moments
+    (pynmap.py:342-419, smear=False) with numpy's global generator seeded before each call."""
+    pos, vel, mass = toy_snapshot(3000, 9, np.float64)
+    rng = np.random.default_rng(4)
+    level = rng.integers(6, 11, 3000).astype(np.float64)
+    out = {"pos": pos, "vel": vel, "mass": mass, "level": level, "seed": np.array(1234)}
+    lim = [-12.0, 12.0, -12.0, 12.0]
+    with tempfile.TemporaryDirectory() as tmp:
+        np.savetxt(os.path.join(tmp, "snap.txt"), np.hstack([pos, vel, mass[:, None], level[:, None]]), fmt="%.17g")
+        snap = quiet(ref.pynmap.snapshot, folder=tmp, snap_name="snap.txt", MLrecipe="none",
+                     extra_labels=["mass", "level"], verbose=False)
+    quiet(snap.rotate, PA=30., inclination=60.)
+    with np.errstate(all="ignore"):
+        np.random.seed(1234)
+        a = quiet(snap.amr_velocity_moments, weight_name="mass", box=100., limXY=lim, nXY=32)
+        np.random.seed(1234)
+        b = quiet(snap.amr_velocity_moments, box=100., limXY=lim, nXY=[24, 40])            # unit weights
+        c = quiet(snap.amr_velocity_moments, weight_name="mass", box=100., limXY=lim, nXY=32, spread=False)
+    out.update(M=a.M, V=a.V, S=a.S, Mu=b.M, Vu=b.V, Su=b.S, Mn=c.M, Vn=c.V, Sn=c.S)
+    # spread_amr itself: float32 coordinates / values, integer levels, a stretch, an integer constant
+    x32, w32 = pos[:500, 0].astype(np.float32), mass[:500].astype(np.float32)
+    lev_i = level[:500].astype(np.int64)
+    np.random.seed(77)
+    cr, vr, kr = ref.misc_io.spread_amr([x32, pos[:500, 1]], lev_i, list_val=[w32, lev_i], list_const=[w32, lev_i],
+                                        nsample=7, box=50., stretch=[1., 0.5])
+    out.update(sp_x=cr[0], sp_y=cr[1], sp_w=vr[0], sp_li=vr[1], sp_cw=kr[0], sp_cl=kr[1])
+    save("amr", **out)
 
 
 def _matrix(rot, pa, inc):

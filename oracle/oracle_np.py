@@ -493,3 +493,20 @@ def fit_gh_scipy(x, data, deg_gh=4, err=None):
     gh = np.concatenate(([1.0], sol.x))
     gh[0] = gh_amplitude(data, gausshermite(x, gh), err)
     return gh, float(np.sum(gh_residuals(sol.x, x, data, err) ** 2))
+
+
+# --------------------------------------------------------------------------- AMR spreading (f3)
+def spread_amr(list_coord, level, list_val=(), list_const=(), nsample=10, box=10, stretch=(), uniforms=None):
+    """misc_io.py:184-224.  ``uniforms``: one (nsample * n,) array of U[0,1) deviates per coordinate;
+    None draws them from numpy's global generator exactly as the reference does (:209)."""
+    scales = box / 2.0 ** np.asarray(level)
+    scalesr = np.repeat(scales, nsample)
+    n = len(list_coord[0])
+    stretch = list(stretch) or [1.0] * len(list_coord)
+    coords = []
+    for k, (cx, s) in enumerate(zip(list_coord, stretch)):
+        u = np.random.random_sample((nsample, n)).ravel() if uniforms is None else uniforms[k]
+        coords.append(np.repeat(cx, nsample) + (u - 0.5) * s * scalesr)
+    vals = [np.repeat(v / nsample, nsample) for v in list_val]
+    consts = [np.repeat(c, nsample) for c in list_const]
+    return coords, vals, consts

@@ -13,6 +13,6 @@ there is no CPU fallback.
 """
 __version__ = "0.1.0"
 
-from . import _lib, engine, rotation, losvd, grid, pynmap, hostpath, sharded, ssp, fit_losvd  # noqa: F401
+from . import _lib, engine, rotation, losvd, grid, pynmap, hostpath, sharded, ssp, fit_losvd, amr  # noqa: F401
 from .pynmap import snapshot, SnapMap  # noqa: F401
 from .losvd import LOSVD  # noqa: F401

@@ -478,6 +478,33 @@ int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t
     return PNM_OK;
 }
 
+int pnm_amr_jitter(const void* coord, int dtype, const double* scale_dev, const double* uniform_dev, int64_t n,
+                   int32_t nsample, double stretch, double* out, void* stream) {
+    if (n < 0 || nsample < 1) return fail(PNM_EINVAL, "pnm_amr_jitter: bad sizes");
+    if (n == 0) return PNM_OK;
+    if (!coord || !scale_dev || !uniform_dev || !out) return fail(PNM_EINVAL, "pnm_amr_jitter: null argument");
+    const int64_t total = n * nsample;
+    const int grid = grid_for(total, 256, 16);
+    if (dtype == PNM_F32) pnm::k_amr_jitter<float><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(coord), scale_dev, uniform_dev, total, nsample, stretch, out);
+    else if (dtype == PNM_F64) pnm::k_amr_jitter<double><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const double*>(coord), scale_dev, uniform_dev, total, nsample, stretch, out);
+    else return fail(PNM_EINVAL, "pnm_amr_jitter: dtype %d", dtype);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_amr_repeat(const void* values, int dtype, int64_t n, int32_t nsample, int divide, void* out, void* stream) {
+    if (n < 0 || nsample < 1) return fail(PNM_EINVAL, "pnm_amr_repeat: bad sizes");
+    if (n == 0) return PNM_OK;
+    if (!values || !out || values == out) return fail(PNM_EINVAL, "pnm_amr_repeat: bad buffers");
+    const int64_t total = n * nsample;
+    const int grid = grid_for(total, 256, 16);
+    if (dtype == PNM_F32) pnm::k_amr_repeat<float><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(values), total, nsample, divide ? 1 : 0, static_cast<float*>(out));
+    else if (dtype == PNM_F64) pnm::k_amr_repeat<double><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const double*>(values), total, nsample, divide ? 1 : 0, static_cast<double*>(out));
+    else return fail(PNM_EINVAL, "pnm_amr_repeat: dtype %d", dtype);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
 int pnm_rebin_cube(const double* cube_in, double* cube_out, int32_t nx, int32_t ny, int32_t nv,
                    int32_t factor_x, int32_t factor_y, int mean, void* stream) {
     if (!cube_in || !cube_out || cube_in == cube_out) return fail(PNM_EINVAL, "pnm_rebin_cube: bad buffers");

@@ -126,6 +126,32 @@ __global__ void __launch_bounds__(256) k_fold_maps(void* acc_maps, int64_t per_r
     a[0] = t;
 }
 
+// spread_amr (misc_io.py:184-224): every cell is replicated nsample times.
+//   coordinates: out[k] = c[k / nsample] + ((u[k] - 0.5) * stretch) * scale[k / nsample]   (float64, misc_io.py:209-212)
+//   values     : out[k] = v[k / nsample] / nsample  or  v[k / nsample]                     (input dtype, :216-222)
+template <typename T>
+__global__ void __launch_bounds__(256) k_amr_jitter(const T* __restrict__ c, const double* __restrict__ scale,
+                                                    const double* __restrict__ u, int64_t total, int nsample,
+                                                    double stretch, double* __restrict__ out) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = k / nsample;
+        const double r = __dmul_rn(__dmul_rn(__dsub_rn(u[k], 0.5), stretch), scale[i]);
+        out[k] = __dadd_rn((double)c[i], r);
+    }
+}
+
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_amr_repeat(const T* __restrict__ v, int64_t total, int nsample, int divide,
+                                                    T* __restrict__ out) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+        const T x = v[k / nsample];
+        out[k] = divide ? div_rn(x, (T)nsample) : x;
+    }
+}
+
 // cube accumulator [iv][q] -> reference layout [q][iv] = cube[ix][iy][iv] (grid.py:259) as float64:
 // 32x32 shared-memory tile transpose, both sides coalesced.
 template <int ACC>

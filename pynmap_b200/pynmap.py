@@ -374,6 +374,42 @@ class snapshot(object):
         mydict["inclinations"] = self.inclinations
         return SnapMap(name="Velocity moments", input_dic=mydict)
 
+    def amr_velocity_moments(self, data=None, weights=None, weight_name=None, box=150.,
+                             limXY=default_limXY, nXY=default_npoint, sigfac=10, smear=False, spread=True,
+                             **kwargs):
+        """Velocity moments for AMR gas (pynmap/pynmap.py:342-419): every cell is replicated 10 times
+        inside its footprint box / 2**level (``spread``; numpy's global generator supplies the
+        deviates exactly as in the reference, see amr.py) and gridded with points_2vmaps.
+
+        ``smear=True`` (per-level maps convolved with astropy's ``convolve_fft`` and an explicitly
+        sized, possibly even ``Gaussian2DKernel``, pynmap.py:379-409) is not available: astropy is
+        not part of this stack and that branch cannot be pinned to it."""
+        if not self._check_attrs(['level']):
+            print("ERROR: missing some input info in class")
+            return None
+        if smear:
+            raise NotImplementedError("amr_velocity_moments(smear=True) needs astropy.convolution.convolve_fft")
+        if weight_name is not None:
+            weights = self._select_weight(weight_name)
+        pos, vel = self._materialise()
+        if data is None:
+            data = vel[2]
+        if weights is None:
+            weights = torch.ones(self.npart, dtype=pos[0].dtype, device=pos[0].device)     # np.ones_like(self.mass)
+        if spread:
+            from .amr import spread_amr
+            [x, y], [weightr], [datar, _] = spread_amr([pos[0], pos[1]], self.level, list_val=[weights],
+                                                       list_const=[data, self.level], nsample=10, box=box,
+                                                       stretch=[1., 1.])
+        else:
+            x, y, datar, weightr = pos[0], pos[1], data, weights
+        X, Y, M, V, S = points_2vmaps(x, y, datar, weights=weightr, limXY=limXY, nXY=nXY)
+        X, Y, M, V, S = (self._conv(a) for a in (X, Y, M, V, S))
+        mydict = {"X": X, "Y": Y, "V": V, "M": M, "S": S}
+        mydict["PAs"] = self.PAs
+        mydict["inclinations"] = self.inclinations
+        return SnapMap(name="Velocity moments", input_dic=mydict)
+
     def _conv(self, a):
         if isinstance(a, torch.Tensor):
             return self._out(a)
