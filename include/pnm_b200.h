@@ -16,6 +16,7 @@
  *   pnm_finalize_cube     weights-histogram -> float64 cube    pynmap/grid.py:259
  *   pnm_smooth_cube       astropy convolve per velocity slice  pynmap/losvd.py:127-135
  *   pnm_cube_moments      moment012 per spaxel                 pynmap/losvd.py:41-51, misc_functions.py:70-90
+ *   pnm_radial_profiles   point_2vprofiles                     pynmap/grid.py:16-68
  *   pnm_amr_jitter/repeat spread_amr                           pynmap/misc_io.py:184-224
  *   pnm_fit_gh            fitgh (mpfit) per spaxel             pynmap/losvd.py:53-67, fit_losvd.py:57-235
  *   pnm_absmax            (new) bound for the fixed-point scale
@@ -209,6 +210,21 @@ int pnm_cube_moments(const double* cube, int32_t nx, int32_t ny, int32_t nv,
 int pnm_amr_jitter(const void* coord, int dtype, const double* scale_dev, const double* uniform_dev, int64_t n,
                    int32_t nsample, double stretch, double* out, void* stream);
 int pnm_amr_repeat(const void* values, int dtype, int64_t n, int32_t nsample, int divide, void* out, void* stream);
+
+/* ---- radial profiles of the velocity ellipsoid (grid.py:16-68 point_2vprofiles; pynmap.py:457-474)
+ * Particles with mask != 0 (mask may be NULL) and z_lo < z < z_hi; R = sqrt(x^2 + y^2) rounded in the
+ * particle dtype; bin = np.digitize(R, rbin) over nbins increasing float64 radii (bin 0: R < rbin[0];
+ * R >= rbin[nbins-1] dropped, as the reference's loop does); VR = Vx cos + Vy sin, VT = -Vx sin + Vy cos
+ * with cos = x / R, sin = y / R.  v, s: float32 [3][nbins] = mean and std (ddof 0) of (VR, VT, Vz),
+ * NaN for an empty bin; counts: int64 [nbins] or NULL.  acc: workspace of pnm_profile_acc_elems(nbins)
+ * float64 (cleared by the call).  pnm_profile_rmax: max R of the selected particles -> out_dev[0]
+ * (float64), the reference's default outer radius (grid.py:51).                                   */
+int64_t pnm_profile_acc_elems(int32_t nbins);
+int pnm_profile_rmax(const void* x, const void* y, const void* z, const uint8_t* mask, int64_t n, int dtype,
+                     double z_lo, double z_hi, double* out_dev, void* stream);
+int pnm_radial_profiles(const void* x, const void* y, const void* z, const void* vx, const void* vy, const void* vz,
+                        const uint8_t* mask, int64_t n, int dtype, double z_lo, double z_hi, const double* rbin_dev,
+                        int32_t nbins, double* acc, float* v, float* s, int64_t* counts, void* stream);
 
 /* ---- f4: Gauss-Hermite fit of every spaxel (losvd.py:53-67, fit_losvd.py:57-235) -------------
  * For each of the nspax profiles cube[s][0..nv) minimise sum(((d - A u(p)) / err)^2) over

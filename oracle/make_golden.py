@@ -17,6 +17,7 @@ import io
 import os
 import sys
 import tempfile
+import warnings
 
 import numpy as np
 
@@ -178,6 +179,7 @@ def main():
 
     make_fit_golden(ref, save)
     make_amr_golden(ref, save)
+    make_profiles_golden(ref, save)
 
     for k, v in saved.items():
         print("%-16s %8.1f kB (uncompressed)" % (k, v / 1e3))
@@ -284,6 +286,23 @@ def make_amr_golden(ref, save):
                                         nsample=7, box=50., stretch=[1., 0.5])
     out.update(sp_x=cr[0], sp_y=cr[1], sp_w=vr[0], sp_li=vr[1], sp_cw=kr[0], sp_cl=kr[1])
     save("amr", **out)
+
+
+def make_profiles_golden(ref, save):
+    """grid.point_2vprofiles (grid.py:16-68).  One float32 particle set is stored; the float64 case
+    runs on its exact upcast."""
+    pos32, vel32, _ = toy_snapshot(20000, 13, np.float32)
+    out = {"pos": pos32, "vel": vel32}
+    for dt in (np.float32, np.float64):
+        pos, vel = pos32.astype(dt), vel32.astype(dt)
+        tag = np.dtype(dt).name
+        with np.errstate(all="ignore"), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            Rbin, v, s = ref.grid.point_2vprofiles(pos[:, 0], pos[:, 1], pos[:, 2], vel[:, 0], vel[:, 1], vel[:, 2], nbins=40)
+            Rb2, v2, s2 = ref.grid.point_2vprofiles(pos[:, 0], pos[:, 1], pos[:, 2], vel[:, 0], vel[:, 1], vel[:, 2], nbins=25,
+                                                    dz=np.array([-0.5, 0.1]), Rmin=0.05, Rmax=20.0)
+        out.update({"Rbin_" + tag: Rbin, "v_" + tag: v, "s_" + tag: s, "Rbin2_" + tag: Rb2, "v2_" + tag: v2, "s2_" + tag: s2})
+    save("profiles", **out)
 
 
 def _matrix(rot, pa, inc):

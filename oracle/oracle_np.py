@@ -510,3 +510,31 @@ def spread_amr(list_coord, level, list_val=(), list_const=(), nsample=10, box=10
     vals = [np.repeat(v / nsample, nsample) for v in list_val]
     consts = [np.repeat(c, nsample) for c in list_const]
     return coords, vals, consts
+
+
+# --------------------------------------------------------------------------- radial profiles
+def point_2vprofiles(x, y, z, Vx, Vy, Vz, nbins=100, dz=(-0.2, 0.2), Rmin=1.e-2, Rmax=None):
+    """grid.py:16-68 (with rotation.xy_to_polar, rotation.py:121-144, for its default PA): numpy's own
+    float32 / float64 arithmetic, mean() and std() per np.digitize bin."""
+    s = np.zeros((3, nbins), dtype=np.float32)
+    v = np.zeros_like(s)
+    sel = np.where((dz[0] < z) & (z < dz[1]))
+    x, y = x[sel], y[sel]
+    R = np.sqrt(x ** 2 + y ** 2)
+    theta = np.arctan2(y, x)
+    VR = Vx[sel] * np.cos(theta) + Vy[sel] * np.sin(theta)
+    VT = -Vx[sel] * np.sin(theta) + Vy[sel] * np.cos(theta)
+    VZ = Vz[sel]
+    if Rmax is None:
+        Rmax = R.max()
+    Rbin = np.logspace(np.log10(Rmin), np.log10(Rmax), nbins)
+    digit = np.digitize(R, Rbin)
+    counts = np.zeros(nbins, dtype=np.int64)
+    with np.errstate(all="ignore"):
+        for i in range(nbins):
+            idx = np.where(digit == i)[0]
+            counts[i] = idx.size
+            for c, comp in enumerate((VR, VT, VZ)):
+                s[c, i] = comp[idx].std()
+                v[c, i] = comp[idx].mean()
+    return Rbin, v, s, counts

@@ -42,6 +42,10 @@ _SIGNATURES = {
     "pnm_smooth_cube": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, POINTER(c_double), c_int32,
                                 POINTER(c_double), c_int32, _P]),
     "pnm_cube_moments": (c_int, [_P, c_int32, c_int32, c_int32, _P, c_double, _P, _P, _P, _P]),
+    "pnm_profile_acc_elems": (c_int64, [c_int32]),
+    "pnm_profile_rmax": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_double, c_double, _P, _P]),
+    "pnm_radial_profiles": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_double, c_double, _P, c_int32,
+                                    _P, _P, _P, _P, _P]),
     "pnm_amr_jitter": (c_int, [_P, c_int, _P, _P, c_int64, c_int32, c_double, _P, _P]),
     "pnm_amr_repeat": (c_int, [_P, c_int, c_int64, c_int32, c_int, _P, _P]),
     "pnm_fit_gh": (c_int, [_P, _P, c_int64, c_int32, _P, c_int32, POINTER(c_double), POINTER(c_double),

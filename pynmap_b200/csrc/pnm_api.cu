@@ -10,6 +10,7 @@
 #include "pnm_bin.cuh"
 #include "pnm_post.cuh"
 #include "pnm_fit.cuh"
+#include "pnm_profile.cuh"
 
 namespace {
 
@@ -501,6 +502,50 @@ int pnm_amr_repeat(const void* values, int dtype, int64_t n, int32_t nsample, in
     if (dtype == PNM_F32) pnm::k_amr_repeat<float><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(values), total, nsample, divide ? 1 : 0, static_cast<float*>(out));
     else if (dtype == PNM_F64) pnm::k_amr_repeat<double><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const double*>(values), total, nsample, divide ? 1 : 0, static_cast<double*>(out));
     else return fail(PNM_EINVAL, "pnm_amr_repeat: dtype %d", dtype);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int64_t pnm_profile_acc_elems(int32_t nbins) {
+    return nbins < 1 ? 0 : (int64_t)pnm::kProfileReplicas * nbins * pnm::kProfileSlots;
+}
+
+int pnm_profile_rmax(const void* x, const void* y, const void* z, const uint8_t* mask, int64_t n, int dtype,
+                     double z_lo, double z_hi, double* out_dev, void* stream) {
+    if (!out_dev || n < 0 || (n > 0 && (!x || !y || !z))) return fail(PNM_EINVAL, "pnm_profile_rmax: bad argument");
+    PNM_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), as_stream(stream)));
+    if (n == 0) return PNM_OK;
+    const int grid = grid_for(n, 256, 8);
+    auto* out = reinterpret_cast<unsigned long long*>(out_dev);
+    if (dtype == PNM_F32) pnm::k_profile_rmax<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, (const float*)y, (const float*)z, mask, n, z_lo, z_hi, out);
+    else if (dtype == PNM_F64) pnm::k_profile_rmax<double><<<grid, 256, 0, as_stream(stream)>>>((const double*)x, (const double*)y, (const double*)z, mask, n, z_lo, z_hi, out);
+    else return fail(PNM_EDTYPE, "pnm_profile_rmax: dtype %d", dtype);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_radial_profiles(const void* x, const void* y, const void* z, const void* vx, const void* vy, const void* vz,
+                        const uint8_t* mask, int64_t n, int dtype, double z_lo, double z_hi, const double* rbin_dev,
+                        int32_t nbins, double* acc, float* v, float* s, int64_t* counts, void* stream) {
+    if (n < 0 || nbins < 1) return fail(PNM_EINVAL, "pnm_radial_profiles: bad sizes");
+    if (nbins > pnm::kProfileMaxBins) return fail(PNM_ELIMIT, "pnm_radial_profiles: more than %d bins", pnm::kProfileMaxBins);
+    if (!rbin_dev || !acc || !v || !s) return fail(PNM_EINVAL, "pnm_radial_profiles: null argument");
+    if (n > 0 && (!x || !y || !z || !vx || !vy || !vz)) return fail(PNM_EINVAL, "pnm_radial_profiles: null particle array");
+    cudaStream_t st = as_stream(stream);
+    PNM_CUDA(cudaMemsetAsync(acc, 0, sizeof(double) * pnm_profile_acc_elems(nbins), st));
+    if (n > 0) {
+        const int grid = grid_for(n, 256, 8);
+        const size_t smem = sizeof(double) * nbins;
+        if (dtype == PNM_F32)
+            pnm::k_profile_acc<float><<<grid, 256, smem, st>>>((const float*)x, (const float*)y, (const float*)z, (const float*)vx,
+                                                              (const float*)vy, (const float*)vz, mask, n, z_lo, z_hi, rbin_dev, nbins, acc);
+        else if (dtype == PNM_F64)
+            pnm::k_profile_acc<double><<<grid, 256, smem, st>>>((const double*)x, (const double*)y, (const double*)z, (const double*)vx,
+                                                               (const double*)vy, (const double*)vz, mask, n, z_lo, z_hi, rbin_dev, nbins, acc);
+        else return fail(PNM_EDTYPE, "pnm_radial_profiles: dtype %d", dtype);
+        PNM_CUDA(cudaGetLastError());
+    }
+    pnm::k_profile_final<<<(nbins + 127) / 128, 128, 0, st>>>(acc, nbins, v, s, reinterpret_cast<long long*>(counts));
     PNM_CUDA(cudaGetLastError());
     return PNM_OK;
 }

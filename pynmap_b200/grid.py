@@ -1,5 +1,5 @@
 """Gridding layer with the reference's signatures (pynmap/grid.py:70-262):
-``points_2vmaps``, ``points_2map``, ``points_2losvds``.  Bodies run on the GPU through
+``points_2vmaps``, ``points_2map``, ``points_2losvds``, ``point_2vprofiles``.  Bodies run on the GPU through
 libpnm_b200 (pnm_bin_points + pnm_finalize_*); numpy in -> numpy out, CUDA tensors in ->
 CUDA tensors out.  The extra keyword ``accumulate`` ('f64' default, 'fixed' = int64
 fixed point) is the only addition to the reference's call surface.
@@ -43,6 +43,35 @@ def _scales_for(acc, n, w, d):
 
 def _mesh(grid, want_torch):
     return grid.mesh(want_torch)
+
+
+def point_2vprofiles(x, y, z, Vx, Vy, Vz, nbins=100, dz=np.array([-0.2, 0.2]), Rmin=1.e-2, Rmax=None, Vmax=None,
+                     plot=False, saveplot=False, **kwargs):
+    """Mean and dispersion of (V_R, V_theta, V_z) in log-spaced radial bins for particles close to the
+    equatorial plane (pynmap/grid.py:16-68).  Returns Rbin (nbins,) float64, v and s (3, nbins) float32;
+    empty bins are NaN.  One pass on the GPU (pnm_radial_profiles) instead of a Python loop over bins."""
+    if plot:
+        raise NameError("name 'plot_sigma' is not defined")        # grid.py:65: the reference's own failure
+    mask = kwargs.pop("mask", None)
+    (xd, yd, zd, vxd, vyd, vzd), m, want_torch, dtype = _prepare([x, y, z, Vx, Vy, Vz], mask)
+    n = xd.numel()
+    code = _lib.F32 if dtype == torch.float32 else _lib.F64
+    z_lo, z_hi = float(dz[0]), float(dz[1])
+    st = engine.stream_ptr()
+    if Rmax is None:                                               # R.max() of the selected particles (grid.py:51)
+        rmax_d = torch.empty(1, dtype=torch.float64, device=xd.device)
+        _lib.call("pnm_profile_rmax", engine.ptr(xd), engine.ptr(yd), engine.ptr(zd), engine.ptr(m), n, code,
+                  z_lo, z_hi, engine.ptr(rmax_d), st)
+        Rmax = np.float32(rmax_d.item()) if dtype == torch.float32 else np.float64(rmax_d.item())
+    Rbin = np.logspace(np.log10(Rmin), np.log10(Rmax), nbins)      # grid.py:52, numpy's dtype rules
+    rbin_d = engine.to_device(np.asarray(Rbin, dtype=np.float64), torch.float64, xd.device)
+    acc = torch.empty(int(_lib.load().pnm_profile_acc_elems(int(nbins))), dtype=torch.float64, device=xd.device)
+    v = torch.empty((3, nbins), dtype=torch.float32, device=xd.device)
+    s = torch.empty((3, nbins), dtype=torch.float32, device=xd.device)
+    _lib.call("pnm_radial_profiles", engine.ptr(xd), engine.ptr(yd), engine.ptr(zd), engine.ptr(vxd), engine.ptr(vyd),
+              engine.ptr(vzd), engine.ptr(m), n, code, z_lo, z_hi, engine.ptr(rbin_d), int(nbins), engine.ptr(acc),
+              engine.ptr(v), engine.ptr(s), None, st)
+    return Rbin, engine.to_output(v, want_torch), engine.to_output(s, want_torch)
 
 
 def points_2vmaps(x, y, v, weights=None, limXY=[-1, 1, -1, 1], nXY=11, mask=None, accumulate="f64"):

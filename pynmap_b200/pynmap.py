@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib, engine
-from .grid import points_2losvds, points_2map, points_2vmaps
+from .grid import point_2vprofiles, points_2losvds, points_2map, points_2vmaps
 from .losvd import LOSVD
 from .rotation import rotation_matrix
 
@@ -409,6 +409,15 @@ class snapshot(object):
         mydict["PAs"] = self.PAs
         mydict["inclinations"] = self.inclinations
         return SnapMap(name="Velocity moments", input_dic=mydict)
+
+    def get_tensor_profiles(self, nbins=100, dz=np.array([-0.2, 0.2]), Rmin=1.e-2, Rmax=None, Vmax=None,
+                            plot=False, saveplot=False, **kwargs):
+        """Radial profiles of the three velocity means and dispersions in cylindrical coordinates
+        (pynmap/pynmap.py:457-474 -> grid.point_2vprofiles)."""
+        pos, vel = self._materialise()
+        Rbin, v, s = point_2vprofiles(pos[0], pos[1], pos[2], vel[0], vel[1], vel[2], nbins=nbins, dz=dz, Rmin=Rmin,
+                                      Rmax=Rmax, Vmax=Vmax, plot=plot, saveplot=saveplot, **kwargs)
+        return Rbin, self._conv(v), self._conv(s)
 
     def _conv(self, a):
         if isinstance(a, torch.Tensor):
