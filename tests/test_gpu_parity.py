@@ -409,3 +409,50 @@ def test_full_size_properties(pnm):
                           omaps[0][..., :3])
     assert np.array_equal(engine.finalize_cube(grid, cube_s, fx, scales).cpu().numpy(),
                           ocube[0].astype(np.float64) * (1.0 / scales[0]))
+
+
+# ------------------------------------------------------------------------------- compiled-in limits
+def test_maximum_sizes_and_limit_errors(pnm):
+    """The largest grids the ABI accepts (PNM_MAX_EDGES - 1 = 4096 bins on an axis, PNM_MAX_TAPS taps,
+    PNM_MAX_CHAIN compounded rotations) still match the oracle; one more is refused loudly."""
+    from pynmap_b200 import _lib, engine
+    rng = np.random.default_rng(12)
+    n = 300_000
+    x = rng.normal(0, 3, n).astype(np.float32)
+    y = rng.normal(0, 3, n).astype(np.float32)
+    d = rng.normal(0, 100, n).astype(np.float32)
+    w = rng.uniform(0.5, 2, n).astype(np.float32)
+    lim = [-6, 6, -6, 6]
+    nmax = _lib.MAX_EDGES - 1
+    for nxy in ([nmax, 8], [8, nmax]):
+        _, _, M, V, S = pnm.grid.points_2vmaps(x, y, d, weights=w, limXY=lim, nXY=nxy, accumulate="fixed")
+        _, _, Mo, Vo, So = on.points_2vmaps(x, y, d, weights=w, limXY=lim, nXY=nxy)
+        assert M.shape == (nxy[1], nxy[0]) and same(M == 0, Mo == 0) and rel_err(M, Mo) < 1e-6
+    lv = pnm.grid.points_2losvds(x, y, d, weights=w, limXY=lim, nXY=8, limV=[-400, 400], nV=nmax)
+    assert sums_close(lv.losvd, on.points_2losvds(x, y, d, weights=w, limXY=lim, nXY=8, limV=[-400, 400], nV=nmax)[3])
+    with pytest.raises(_lib.PnmError, match="edges"):
+        pnm.grid.points_2vmaps(x, y, d, limXY=lim, nXY=[nmax + 1, 8])
+    # widest smoothing kernel: support = PNM_MAX_TAPS
+    cube = torch.from_numpy(rng.random((40, 36, 3))).cuda()
+    taps = engine.gaussian_taps(_lib.MAX_TAPS / 8.0, _lib.MAX_TAPS)
+    out = engine.smooth_cube(cube, taps, taps).cpu().numpy()
+    ker = np.outer(taps, taps)
+    ref = np.stack([on.convolve2d_fill0(cube[:, :, k].cpu().numpy(), ker) for k in range(3)], axis=2)
+    assert rel_err(out, ref, floor=1e-12) < 1e-11
+    with pytest.raises(_lib.PnmError, match="taps"):
+        engine.smooth_cube(cube, np.ones(_lib.MAX_TAPS + 2) / (_lib.MAX_TAPS + 2), taps)
+    # longest rotation chain: 8 compounded rotate(reset=False) calls, then one too many
+    pos = rng.normal(0, 3, (5000, 3)).astype(np.float32)
+    vel = rng.normal(0, 100, (5000, 3)).astype(np.float32)
+    snap = pnm.snapshot.from_arrays(pos, vel, mass=np.ones(5000, dtype=np.float32))
+    p_ref, v_ref = pos, vel
+    for k in range(_lib.MAX_CHAIN):
+        snap.rotate(PA=10. + k, inclination=20. + 3 * k, reset=False)
+        p_ref, v_ref = on.rotate_mat(p_ref, v_ref, np.float32(10. + k), np.float32(20. + 3 * k))
+    vm = snap.velocity_moments(limXY=lim, nXY=24, accumulate="fixed")
+    _, _, Mo, Vo, So = on.points_2vmaps(p_ref[:, 0], p_ref[:, 1], v_ref[:, 2], limXY=lim, nXY=24)
+    assert same(vm.M, Mo)                                   # counts: bit-exact through 8 roundings
+    snap.rotate(PA=1., inclination=2., reset=False)         # a ninth: the chain is folded by materialising
+    p_ref, v_ref = on.rotate_mat(p_ref, v_ref, np.float32(1.), np.float32(2.))
+    vm9 = snap.velocity_moments(limXY=lim, nXY=24, accumulate="fixed")
+    assert same(vm9.M, on.points_2vmaps(p_ref[:, 0], p_ref[:, 1], v_ref[:, 2], limXY=lim, nXY=24)[2])
