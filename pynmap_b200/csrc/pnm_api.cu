@@ -289,7 +289,7 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     p.replicas = g->replicas;
     p.rep_shift = env_int("PNM_REP_SHIFT", 5);
     // hybrid scatter: 16-byte TMA bulk reductions need a 16-byte aligned maps accumulator
-    p.tma_slots = (acc_maps && (reinterpret_cast<uintptr_t>(acc_maps) & 15) == 0)
+    p.tma_slots = (acc_maps && (reinterpret_cast<uintptr_t>(acc_maps) & 15) == 0 && (sums & PNM_SUM_WD) && (sums & PNM_SUM_WD2))
                       ? std::max(0, std::min(env_int("PNM_TMA_SLOTS", (sums & PNM_SUM_CUBE) ? 3 : 4), pnm::kTmaSlots)) : 0;
     // (measured, 1e8 particles: maps+cube 1.78 / 1.60 / 1.62 / 1.74 ms and 256^2 maps only
     //  2.01 / 1.52 / 1.47 / 1.59 ms for 0 / 3 / 4 / 5 of the 8 updates of a tile through the TMA unit)
