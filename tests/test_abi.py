@@ -65,6 +65,15 @@ def test_no_cpu_fallback():
         pynmap_b200.rotation.rotate_mat(np.zeros((4, 3), dtype=np.float32), None, 30., 60.)
     with pytest.raises(_lib.PnmError):
         pynmap_b200.snapshot.from_arrays(np.zeros((4, 3)), np.zeros((4, 3)))
+    v = np.linspace(-100.0, 100.0, 32)
+    with pytest.raises(_lib.PnmError):
+        pynmap_b200.fit_losvd.fitgh(v, np.exp(-v * v / 800.0), deg_gh=4, verbose=False)
+    with pytest.raises(_lib.PnmError):
+        pynmap_b200.LOSVD(v[:4], v[:4], v, np.zeros((4, 4, 32))).fitlosvd()
+    with pytest.raises(_lib.PnmError):
+        pynmap_b200.amr.spread_amr([v], np.full(32, 5), nsample=2)
+    with pytest.raises(_lib.PnmError):
+        pynmap_b200.grid.point_2vprofiles(v, v, v * 0, v, v, v, nbins=5)
 
 
 def test_product_never_imports_oracle():
