@@ -1,0 +1,128 @@
+"""Container-only cross-check: the oracle against the UNMODIFIED reference executed live (through
+oracle/refshim.py) on fresh seeded inputs, beyond the frozen vectors of tests/golden/.  Skipped
+wherever /root/reference is absent (the GPU box), so nothing in the `-m gpu` run depends on it."""
+import contextlib
+import io
+import warnings
+
+import numpy as np
+import pytest
+
+from oracle import oracle_np as on
+from oracle import refshim
+
+pytestmark = pytest.mark.skipif(not refshim.reference_available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return refshim.load_reference()
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings(), np.errstate(all="ignore"):
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
+
+
+def same(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and np.array_equal(a, b, equal_nan=True)
+
+
+def particles(seed, n, dtype):
+    rng = np.random.default_rng(seed)
+    pos = (rng.standard_normal((n, 3)) * [4.0, 4.0, 0.6]).astype(dtype)
+    vel = (rng.standard_normal((n, 3)) * 120.0 + [0.0, 150.0, 0.0]).astype(dtype)
+    mass = rng.uniform(0.2, 3.0, n).astype(dtype)
+    return pos, vel, mass
+
+
+@pytest.mark.parametrize("seed,dtype", [(101, np.float32), (202, np.float64), (303, np.float32)])
+def test_rotation_live(ref, seed, dtype):
+    pos, vel, _ = particles(seed, 3000, dtype)
+    rng = np.random.default_rng(seed)
+    for direct in (True, False):
+        pa, inc = rng.uniform(-180, 180), rng.uniform(0, 180)
+        p_ref, v_ref = ref.rotation.rotate_mat(pos, vel, pa, inc, direct=direct)
+        p, v = on.rotate_mat(pos, vel, pa, inc, direct=direct)
+        assert same(p, p_ref) and same(v, v_ref)
+        a, b, c = rng.uniform(-90, 90, 3)
+        p_ref, v_ref = ref.rotation.rotateXYZ_mat(pos, vel, a, b, c, direct=direct)
+        mat = on.rotation_matrix_xyz(a, b, c, direct=direct)
+        assert same(np.stack(on.rotate_soa(mat, pos[:, 0], pos[:, 1], pos[:, 2]), 1), p_ref)
+
+
+@pytest.mark.parametrize("seed,dtype", [(11, np.float32), (12, np.float64)])
+def test_gridding_live(ref, seed, dtype):
+    pos, vel, mass = particles(seed, 20000, dtype)
+    x, y, d = pos[:, 0], pos[:, 1], vel[:, 2].copy()
+    d[::97] = np.nan
+    x = x.copy()
+    x[5] = np.inf
+    lim = [-9.0, 7.0, -6.0, 8.0]
+    mask = np.zeros(x.size, bool)
+    mask[::5] = True
+    for nxy in (17, [24, 10]):
+        got = quiet(on.points_2vmaps, x, y, d, weights=mass, limXY=lim, nXY=nxy, mask=mask)
+        want = quiet(ref.grid.points_2vmaps, x, y, d, weights=mass, limXY=lim, nXY=nxy, mask=mask)
+        assert all(same(g, w) for g, w in zip(got, want))
+        got = quiet(on.points_2map, x, y, data=d, weights=mass, limXY=lim, nXY=nxy)
+        want = quiet(ref.grid.points_2map, x, y, data=d, weights=mass, limXY=lim, nXY=nxy)
+        assert all(same(g, w) for g, w in zip(got, want))
+    lv = quiet(ref.grid.points_2losvds, x, y, d, weights=mass, limXY=lim, nXY=[12, 9], limV=[-300.0, 420.0], nV=21)
+    px, py, pv, cube = quiet(on.points_2losvds, x, y, d, weights=mass, limXY=lim, nXY=[12, 9], limV=[-300.0, 420.0], nV=21)
+    assert same(cube, lv.losvd) and same(pv, lv.binv) and same(px, lv.binx) and same(py, lv.biny)
+
+
+def test_cube_post_processing_live(ref):
+    pos, vel, mass = particles(5, 30000, np.float64)
+    lim = [-8.0, 8.0, -8.0, 8.0]
+    lv = quiet(ref.grid.points_2losvds, pos[:, 0], pos[:, 1], vel[:, 2], weights=mass, limXY=lim, nXY=16,
+               limV=[-400.0, 400.0], nV=24)
+    quiet(lv.vmoments)
+    m = np.array([[on.moment012(lv.binv, lv.losvd[i, j]) for j in range(16)] for i in range(16)])
+    assert same(m[..., 0], lv.mom0) and same(m[..., 1], lv.mom1) and same(m[..., 2], lv.mom2)
+    sm = quiet(lv.convolve_spatial, 1.7, 2.9)
+    assert np.allclose(on.convolve_spatial(lv.losvd, lv.stepx, lv.stepy, 1.7, 2.9)[0], sm.losvd, rtol=1e-13, atol=1e-13)
+    rb = quiet(lv.rebin_spatial, 2, 4, "mean")
+    bx, by, cube = on.rebin_spatial(lv.losvd, lv.binx, lv.biny, 2, 4, "mean")
+    assert same(cube, rb.losvd) and same(bx, rb.binx) and same(by, rb.biny)
+
+
+def test_gauss_hermite_objective_live(ref):
+    mf, fl = ref.misc_functions, ref.fit_losvd
+    rng = np.random.default_rng(8)
+    x = np.linspace(-480.0, 480.0, 49)
+    for deg in (2, 3, 4, 5, 6):
+        gh = np.r_[rng.uniform(1, 50), rng.uniform(-100, 100), rng.uniform(30, 120), rng.uniform(-0.2, 0.2, deg - 2)]
+        assert same(on.gausshermite(x, gh), quiet(mf.gausshermite, x, gh))
+        data = rng.poisson(np.maximum(mf.gausshermite(x, gh), 0)).astype(np.float64)
+        err = np.sqrt(np.maximum(data, 1.0))
+        u = mf.gausshermite(x, np.r_[1.0, gh[1:]])
+        assert on.gh_amplitude(data, u) == fl._solve_amplitude(data, u)
+        assert on.gh_amplitude(data, u, err) == fl._solve_amplitude(data, u, err)
+        assert same(on.gh_residuals(gh[1:], x, data, err), fl._fitGH_residuals_err(
+            np.r_[fl._solve_amplitude(data, u, err), gh[1:]], x, data, err))
+        p0, lo, hi = on.gh_guess_and_limits(x, data, deg)
+        assert same(np.array(on.moment012(x, data)[1:]), p0[:2])
+    got = on.fit_gh_scipy(x, data, 6)[0]
+    want = quiet(fl.fitgh, x, data, deg_gh=6, verbose=False)[0]
+    scale = np.r_[want[0], want[2], want[2], np.ones(4)]
+    assert np.max(np.abs(got - want) / scale) < 2e-5
+
+
+def test_amr_and_profiles_live(ref):
+    pos, vel, mass = particles(21, 8000, np.float32)
+    level = np.random.default_rng(3).integers(5, 12, 8000)
+    np.random.seed(99)
+    want = ref.misc_io.spread_amr([pos[:, 0], pos[:, 1]], level, list_val=[mass], list_const=[vel[:, 2], level],
+                                  nsample=6, box=80., stretch=[1., 2.])
+    np.random.seed(99)
+    got = on.spread_amr([pos[:, 0], pos[:, 1]], level, [mass], [vel[:, 2], level], nsample=6, box=80., stretch=[1., 2.])
+    for g_list, w_list in zip(got, want):
+        assert all(same(g, w) for g, w in zip(g_list, w_list))
+    cols = [pos[:, 0], pos[:, 1], pos[:, 2], vel[:, 0], vel[:, 1], vel[:, 2]]
+    Rb, v, s = quiet(ref.grid.point_2vprofiles, *cols, nbins=30, dz=np.array([-0.4, 0.3]))
+    Ro, vo, so, _ = quiet(on.point_2vprofiles, *cols, nbins=30, dz=(-0.4, 0.3))
+    assert same(Ro, Rb) and same(vo, v) and same(so, s)
