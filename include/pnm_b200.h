@@ -70,6 +70,13 @@ extern "C" {
  * directly: particles inside the V range go to the cube only, the others to maps slot 0,
  * and pnm_finalize_vmaps adds the cube's V-sum back.  One atomic fewer per particle.       */
 #define PNM_W_FROM_CUBE 16
+/* Mixed input dtypes (pnm_bin_points with dtype = PNM_F64 only).  numpy evaluates `wm * vm` and
+ * `wm * vm**2` (grid.py:128-131, :201) in the result type of the two operands, which is float32 when
+ * both are float32 even if the coordinates are float64.  Arrays are still passed as float64:
+ *   PNM_VAL_D32: d holds float32 values, d*d is rounded in float32;
+ *   PNM_VAL_W32: w holds float32 values too; with both set w*d and w*(d*d) are rounded in float32.  */
+#define PNM_VAL_D32 64
+#define PNM_VAL_W32 128
 /* pnm_finalize_vmaps only: the first map replica already holds the totals (pnm_fold_maps, possibly
  * followed by a reduction over ranks); the other replicas are not read.                          */
 #define PNM_MAPS_FOLDED 32

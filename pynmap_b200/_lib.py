@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("PNM_B200_LIB", os.path.join(_HERE, "libpnm_b200.so"))
 # constants mirrored from include/pnm_b200.h
 F32, F64 = 0, 1
 ACC_F64, ACC_FIXED = 0, 1
-SUM_W, SUM_WD, SUM_WD2, SUM_CUBE, W_FROM_CUBE, MAPS_FOLDED = 1, 2, 4, 8, 16, 32
+SUM_W, SUM_WD, SUM_WD2, SUM_CUBE, W_FROM_CUBE, MAPS_FOLDED, VAL_D32, VAL_W32 = 1, 2, 4, 8, 16, 32, 64, 128
 MASK_NONE, MASK_AND_NONFINITE, MASK_PLAIN = 0, 1, 2
 MAX_EDGES, MAX_CHAIN, MAX_VIEWS, MAX_TAPS, MAP_SLOTS = 4097, 8, 64, 255, 4
 MAX_MATS = 64

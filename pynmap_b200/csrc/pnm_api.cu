@@ -263,6 +263,8 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     if ((sums & PNM_SUM_CUBE) && (!acc_cube || g->nv < 1)) return fail(PNM_EINVAL, "%s: cube requested without cube accumulator / V axis", who);
     if ((sums & PNM_W_FROM_CUBE) && !((sums & PNM_SUM_CUBE) && (sums & PNM_SUM_W)))
         return fail(PNM_EINVAL, "%s: PNM_W_FROM_CUBE needs PNM_SUM_W|PNM_SUM_CUBE", who);
+    if ((sums & (PNM_VAL_D32 | PNM_VAL_W32)) && (fused || dtype != PNM_F64))
+        return fail(PNM_EINVAL, "%s: PNM_VAL_D32 / PNM_VAL_W32 describe float32 values carried as float64 (pnm_bin_points, PNM_F64)", who);
     if (mask_mode != PNM_MASK_NONE && !mask) return fail(PNM_EINVAL, "%s: mask_mode without mask", who);
     if (mask_mode < 0 || mask_mode > 2) return fail(PNM_EINVAL, "%s: mask_mode %d", who, mask_mode);
     if (fused) {

@@ -262,8 +262,16 @@ struct Binner {
         const bool in_v = want_v && (unsigned)iv < (unsigned)av.n;
         if (sm & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2)) {
             const bool use0 = (sm & PNM_SUM_W) && !((sm & PNM_W_FROM_CUBE) && in_v);
+            T dd = mul_rn(d, d), wd, wdd;
+            if (sizeof(T) == 8 && (sm & PNM_VAL_D32)) {         // numpy rounds `vm**2` in the dtype of v (grid.py:131)
+                dd = (T)__fmul_rn((float)d, (float)d);
+                if (sm & PNM_VAL_W32) {                         // ... and `wm * vm`, `wm * vm**2` in float32 when both are
+                    wd = (T)__fmul_rn((float)w, (float)d);
+                    wdd = (T)__fmul_rn((float)w, (float)dd);
+                } else { wd = mul_rn(w, d); wdd = mul_rn(w, dd); }
+            } else { wd = mul_rn(w, d); wdd = mul_rn(w, dd); }
             run.add(maps, sm, st, (iy * nx + ix) * PNM_MAP_SLOTS, use0, to_acc<ACC>(w, sc0),
-                    to_acc<ACC>(mul_rn(w, d), sc1), to_acc<ACC>(mul_rn(w, mul_rn(d, d)), sc2));
+                    to_acc<ACC>(wd, sc1), to_acc<ACC>(wdd, sc2));
         }
         if (in_v) red_add(cube + (iv * npix + ix * ny + iy), to_acc<ACC>(w, sc0));
     }

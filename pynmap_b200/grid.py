@@ -35,6 +35,19 @@ def _prepare(arrays, mask):
     return dev, m, want_torch, dtype
 
 
+def _value_flags(dtype, d, w):
+    """PNM_VAL_D32 / PNM_VAL_W32: numpy's result type for `wm * vm` and `vm**2` (grid.py:128-131) when the
+    coordinates forced float64 transport but the values are float32."""
+    if dtype != torch.float64:
+        return 0
+    flags = 0
+    if d is not None and engine.result_dtype(d) == torch.float32:
+        flags |= _lib.VAL_D32
+        if w is not None and engine.result_dtype(w) == torch.float32:
+            flags |= _lib.VAL_W32
+    return flags
+
+
 def _scales_for(acc, n, w, d):
     if acc.code != _lib.ACC_FIXED:
         return None
@@ -83,13 +96,13 @@ def points_2vmaps(x, y, v, weights=None, limXY=[-1, 1, -1, 1], nXY=11, mask=None
     if n2 is None:
         print("ERROR: dimension of n should be 1 or 2")
         return 0, 0, 0, 0, 0
-    (xd, yd, vd, wd), m, want_torch, _ = _prepare([x, y, v, weights], mask)
+    (xd, yd, vd, wd), m, want_torch, dtype = _prepare([x, y, v, weights], mask)
     grid = engine.get_grid(limXY, n2[0], n2[1])
     acc = engine.AccMode(accumulate)
     sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2
     scales = _scales_for(acc, xd.numel(), wd, vd)
     maps, _ = engine.new_accumulators(grid, sums, acc)
-    engine.bin_points(grid, xd, yd, vd, wd, sums, acc, scales, maps, None, m,
+    engine.bin_points(grid, xd, yd, vd, wd, sums | _value_flags(dtype, v, weights), acc, scales, maps, None, m,
                       _lib.MASK_AND_NONFINITE if m is not None else _lib.MASK_NONE)
     M, V, S = engine.finalize_vmaps(grid, maps, None, sums, acc, scales)
     gx, gy = _mesh(grid, want_torch)
@@ -104,13 +117,13 @@ def points_2map(x, y, data=None, weights=None, limXY=[-1, 1, -1, 1], nXY=10, mas
         return 0, 0, 0, 0, 0
     if data is None:
         data = torch.ones_like(x) if isinstance(x, torch.Tensor) else np.ones_like(x)
-    (xd, yd, dd, wd), m, want_torch, _ = _prepare([x, y, data, weights], mask)
+    (xd, yd, dd, wd), m, want_torch, dtype = _prepare([x, y, data, weights], mask)
     grid = engine.get_grid(limXY, n2[0], n2[1])
     acc = engine.AccMode(accumulate)
     sums = _lib.SUM_W | _lib.SUM_WD
     scales = _scales_for(acc, xd.numel(), wd, dd)
     maps, _ = engine.new_accumulators(grid, sums, acc)
-    engine.bin_points(grid, xd, yd, dd, wd, sums, acc, scales, maps, None, m,
+    engine.bin_points(grid, xd, yd, dd, wd, sums | _value_flags(dtype, data, weights), acc, scales, maps, None, m,
                       _lib.MASK_AND_NONFINITE if m is not None else _lib.MASK_NONE)
     W, D, DW = engine.finalize_map(grid, maps, acc, scales)
     gx, gy = _mesh(grid, want_torch)

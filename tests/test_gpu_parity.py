@@ -456,3 +456,27 @@ def test_maximum_sizes_and_limit_errors(pnm):
     p_ref, v_ref = on.rotate_mat(p_ref, v_ref, np.float32(1.), np.float32(2.))
     vm9 = snap.velocity_moments(limXY=lim, nXY=24, accumulate="fixed")
     assert same(vm9.M, on.points_2vmaps(p_ref[:, 0], p_ref[:, 1], v_ref[:, 2], limXY=lim, nXY=24)[2])
+
+
+def test_mixed_dtypes_follow_numpy_result_types(pnm):
+    """float64 coordinates with float32 values: numpy rounds `wm * vm` and `vm**2` in float32
+    (grid.py:128-131); the kernel carries everything as float64 and is told so (PNM_VAL_D32/W32)."""
+    rng = np.random.default_rng(31)
+    n = 40000
+    x, y = rng.normal(0, 3, n), rng.normal(0, 3, n)                       # float64
+    v32 = rng.normal(0, 150, n).astype(np.float32)
+    w32 = rng.uniform(0.5, 2, n).astype(np.float32)
+    lim = [-6, 6, -6, 6]
+    for v, w in ((v32, w32), (v32, w32.astype(np.float64)), (v32, None), (v32.astype(np.float64), w32)):
+        _, _, M, V, S = pnm.grid.points_2vmaps(x, y, v, weights=w, limXY=lim, nXY=20, accumulate="fixed")
+        _, _, Mo, Vo, So = on.points_2vmaps(x, y, v, weights=w, limXY=lim, nXY=20)
+        ok = Mo > 0
+        assert rel_err(M, Mo) < 1e-12
+        assert np.max(np.abs(V - Vo)[ok]) < 1e-10 * 150 and np.max(np.abs(S**2 - So**2)[ok & (So > 0)]) < 1e-10 * 150**2
+        _, _, W, D, DW = pnm.grid.points_2map(x, y, data=v, weights=w, limXY=lim, nXY=20, accumulate="fixed")
+        _, _, Wo, Do, DWo = on.points_2map(x, y, data=v, weights=w, limXY=lim, nXY=20)
+        assert np.max(np.abs(DW - DWo)) < 1e-10 * np.max(np.abs(DWo))
+    # the distinction is real: exact float64 products differ from numpy's float32 ones at the 1e-8 level
+    _, _, _, V64, _ = on.points_2vmaps(x, y, v32.astype(np.float64), weights=w32.astype(np.float64), limXY=lim, nXY=20)
+    _, _, _, V32, _ = on.points_2vmaps(x, y, v32, weights=w32, limXY=lim, nXY=20)
+    assert np.nanmax(np.abs(V64 - V32)) > 1e-8
