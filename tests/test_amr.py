@@ -77,3 +77,27 @@ def test_gpu_amr_velocity_moments(golden, capsys):
     assert bare.amr_velocity_moments() is None and "missing some input info" in capsys.readouterr().out
     with pytest.raises(NotImplementedError):
         snap.amr_velocity_moments(smear=True)
+
+
+@pytest.mark.gpu
+def test_gpu_amr_float32_snapshot_against_oracle(golden):
+    """float32 particles: the jittered coordinates are float64 while velocities and weights / 10 stay
+    float32, so the weighted terms are float32 products (numpy result types) -- checked against the
+    oracle's restatement of the whole chain on the same seeded deviates."""
+    import pynmap_b200 as pnm
+    g = golden("amr")
+    pos, vel, mass = (g[k].astype(np.float32) for k in ("pos", "vel", "mass"))
+    level = g["level"].astype(np.int64)
+    snap = pnm.snapshot.from_arrays(pos, vel, mass=mass, level=level)
+    snap.rotate(PA=30., inclination=60.)
+    np.random.seed(5)
+    got = snap.amr_velocity_moments(weight_name="mass", box=100., limXY=LIM, nXY=32)
+    p_rot, v_rot = on.rotate_mat(pos, vel, np.float32(30.), np.float32(60.))
+    np.random.seed(5)
+    (x, y), (w,), (d, _) = on.spread_amr([p_rot[:, 0], p_rot[:, 1]], level, [mass], [v_rot[:, 2], level],
+                                          nsample=10, box=100., stretch=[1., 1.])
+    assert x.dtype == np.float64 and d.dtype == np.float32 and w.dtype == np.float32
+    _, _, M, V, S = on.points_2vmaps(x, y, d, weights=w, limXY=LIM, nXY=32)
+    occupied = M > 0
+    assert rel_err(got.M, M) < 1e-12 and np.max(np.abs(got.V - V)[occupied]) < 1e-10 * 300.0
+    assert np.max(np.abs(np.nan_to_num(got.S) ** 2 - np.nan_to_num(S) ** 2)[occupied]) < 1e-10 * 300.0 ** 2
