@@ -200,7 +200,8 @@ class snapshot(object):
     def compute_ml(self):
         """flux = mass / ML (pynmap/pynmap.py:234-236).  The SSP recipe of the reference
         (misc_functions.compute_ml_ssps: scipy griddata on the E-MILES tables) needs those tables,
-        which are data of the reference and are not shipped here: pass
+        which are data of the reference and are not shipped here: they are looked for in $PNM_SSP_DIR and
+        in an installed reference package (ssp.default_ssp_dir), or pass
         ``ml_function=functools.partial(pynmap_b200.ssp.compute_ml_ssps, ssp_dir=<SSPLibraries>)``
         (GPU interpolation), any callable (mass, age, MH) -> M/L, or ``flux=`` to
         from_arrays.  Any other recipe is M/L = 1.  M/L is kept in float64 like the reference's; the
@@ -209,9 +210,14 @@ class snapshot(object):
             ml = self.ml_function(self.mass, self.age, self.MH)
             self.ML = engine.to_device(ml, torch.float64, self.mass.device)
         elif self.MLrecipe == "SSPs":
-            raise NotImplementedError(
-                "MLrecipe='SSPs' needs the reference's SSP tables: pass ml_function=functools.partial("
-                "pynmap_b200.ssp.compute_ml_ssps, ssp_dir=...) or precomputed flux; use MLrecipe=None for M/L = 1")
+            from . import ssp
+            if ssp.default_ssp_dir() is None:
+                raise NotImplementedError(
+                    "MLrecipe='SSPs' needs the reference's SSP tables: set PNM_SSP_DIR, install the reference "
+                    "package, pass ml_function=functools.partial(pynmap_b200.ssp.compute_ml_ssps, ssp_dir=...) or "
+                    "precomputed flux; use MLrecipe=None for M/L = 1")
+            ml = ssp.compute_ml_ssps(self.mass, self.age, self.MH)       # misc_functions.py:92-113 -> :115-207
+            self.ML = engine.to_device(ml, torch.float64, self.mass.device)
         else:
             self.ML = torch.ones_like(self.mass, dtype=torch.float64)
         self.flux = (self.mass.double() / self.ML).to(self.mass.dtype)

@@ -13,6 +13,7 @@ everything per PARTICLE runs in the ``pnm_ct_interp`` kernel: point location thr
 cell -> triangle index, barycentric coordinates, the cubic, and the nearest-node fill.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -202,6 +203,25 @@ def ssp_ml_table(ssp_dir, IMF='KB', slope=1.30, iso='BaSTI', band='V'):
     return m['age'][mw], m['MH'][mw], m['mSRem'][mw] / flux
 
 
+def default_ssp_dir():
+    """Where the E-MILES tables are looked for when ``ssp_dir`` is not given: $PNM_SSP_DIR, else the
+    ``SSPLibraries`` directory of an installed reference package (located, not imported)."""
+    env = os.environ.get("PNM_SSP_DIR")
+    if env:
+        return env
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("pynmap")
+    except (ImportError, ValueError):
+        spec = None
+    if spec is not None and spec.submodule_search_locations:
+        for loc in spec.submodule_search_locations:
+            cand = os.path.join(loc, "SSPLibraries")
+            if os.path.isdir(cand):
+                return cand
+    return None
+
+
 def compute_ml_ssps(mass, age=None, MH=None, ssp_dir=None, IMF='KB', slope=1.30, iso='BaSTI', band='V',
                     fill_nan=True):
     """Drop-in for misc_functions.compute_ml_ssps (:115-207) with the interpolation on the GPU.
@@ -209,6 +229,9 @@ def compute_ml_ssps(mass, age=None, MH=None, ssp_dir=None, IMF='KB', slope=1.30,
     if age is None or MH is None:
         return torch.ones_like(mass) if isinstance(mass, torch.Tensor) else np.ones_like(mass)
     if ssp_dir is None:
-        raise ValueError("ssp_dir: path of the reference's pynmap/SSPLibraries directory is required")
+        ssp_dir = default_ssp_dir()
+    if ssp_dir is None:
+        raise ValueError("ssp_dir: path of the reference's pynmap/SSPLibraries directory is required "
+                         "(or set PNM_SSP_DIR / install the reference package)")
     ages, metals, ml = ssp_ml_table(ssp_dir, IMF, slope, iso, band)
     return MLInterpolator(ages, metals, ml)(age, MH, fill_nan=fill_nan)

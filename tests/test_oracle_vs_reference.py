@@ -126,3 +126,19 @@ def test_amr_and_profiles_live(ref):
     Rb, v, s = quiet(ref.grid.point_2vprofiles, *cols, nbins=30, dz=np.array([-0.4, 0.3]))
     Ro, vo, so, _ = quiet(on.point_2vprofiles, *cols, nbins=30, dz=(-0.4, 0.3))
     assert same(Ro, Rb) and same(vo, v) and same(so, s)
+
+
+def test_ssp_tables_are_found_and_read_like_the_reference(ref, golden, monkeypatch):
+    """MLrecipe='SSPs' drop-in: the tables are located through PNM_SSP_DIR (or an installed reference
+    package) and the host-side reader yields the nodes the reference interpolates (golden 'ssp')."""
+    import os
+    from pynmap_b200 import ssp
+    libdir = os.path.join(refshim.REFERENCE_ROOT, "pynmap", "SSPLibraries")
+    monkeypatch.setenv("PNM_SSP_DIR", libdir)
+    assert ssp.default_ssp_dir() == libdir
+    ages, metals, ml = ssp.ssp_ml_table(ssp.default_ssp_dir())
+    g = golden("ssp")
+    assert np.array_equal(ages, g["node_age"]) and np.array_equal(metals, g["node_MH"])
+    assert np.allclose(ml, g["node_ML"], rtol=1e-15, atol=0)
+    monkeypatch.delenv("PNM_SSP_DIR")
+    assert ssp.default_ssp_dir() == libdir          # the reference package is importable here (refshim put it on sys.path)
