@@ -227,3 +227,61 @@ def test_host_path_single_and_sharded_flavours(env):
     with pytest.raises(ValueError):
         hostpath.project_host([host[k] for k in range(7)], 30., 60., wl.LIM_XY, 64, wl.LIM_V, 32, accumulate="fixed")
     pnm._lib.call("pnm_host_release")
+
+
+def test_sharded_project_with_post_stream_matches_plain(env):
+    """snapshot.project through the sharded code path (fold without clearing, reduce hook, finalise
+    from the folded replica) on a post-processing stream == the plain single-GPU call, and two
+    half-snapshots summed by the hook == the whole snapshot (fixed point: bit-exact)."""
+    import pynmap_b200 as pnm
+    import workloads
+    n = 3_000_000
+    soa = workloads.make_snapshot(n, seed=91, device="cuda")
+    kw = dict(weight_name="mass", limXY=workloads.LIM_XY, nXY=96, limV=workloads.LIM_V, nV=64, accumulate="fixed")
+
+    def snap_of(lo, hi):
+        s = pnm.snapshot.from_arrays(soa[:3, lo:hi], soa[3:6, lo:hi], mass=soa[6, lo:hi], output="torch")
+        s.rotate(PA=30., inclination=60.)
+        return s
+
+    whole = snap_of(0, n)
+    vm0, lv0 = whole.project(**kw)
+    post = torch.cuda.Stream(priority=-1)
+    seen = []
+
+    def hook(*tensors):                                   # world size 1: rank 0 already holds the total
+        seen.append(sum(t.numel() for t in tensors))
+        return True
+    hook.n_total = lambda n_local: n
+    hook.reduce_max = lambda *v: v
+    vm1, lv1 = whole.project(reducer=hook, post_stream=post, **kw)
+    post.synchronize()
+    assert seen == [96 * 96 * 64 + 96 * 96 * 4]           # one contiguous span: cube + the folded map replica
+    for a, b in ((vm0.M, vm1.M), (vm0.V, vm1.V), (vm0.S, vm1.S), (lv0.losvd, lv1.losvd)):
+        assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+
+    # two "ranks": the second adds the first one's span before finalising
+    half = n // 2 + 5
+    parts = {}
+
+    def hook_a(*tensors):
+        parts["a"] = [t.clone() for t in tensors]
+        return False
+    hook_a.n_total = lambda n_local: n
+    hook_a.reduce_max = lambda *v: (max(v[0], bounds[0]), max(v[1], bounds[1]))
+
+    def hook_b(*tensors):
+        for t, other in zip(tensors, parts["a"]):
+            t += other
+        return True
+    hook_b.n_total = hook_a.n_total
+    hook_b.reduce_max = hook_a.reduce_max
+    from pynmap_b200 import engine
+    bounds = (engine.absmax(soa[6]), 2.0 * max(engine.absmax(soa[k]) for k in (3, 4, 5)))
+    assert snap_of(0, half).project(reducer=hook_a, **kw) == (None, None)
+    vm2, lv2 = snap_of(half, n).project(reducer=hook_b, **kw)
+    whole2 = snap_of(0, n)
+    hook.reduce_max = hook_a.reduce_max
+    vm3, lv3 = whole2.project(reducer=hook, **kw)         # same global bounds -> same fixed-point scales
+    for a, b in ((vm3.M, vm2.M), (vm3.V, vm2.V), (vm3.S, vm2.S), (lv3.losvd, lv2.losvd)):
+        assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
