@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libpnm_b200.so")
 SOURCES = ["pnm_api.cu", "pnm_host.cu"]
-HEADERS = ["pnm_common.cuh", "pnm_bin.cuh", "pnm_post.cuh", os.path.join("..", "..", "include", "pnm_b200.h")]
+HEADERS = ["pnm_common.cuh", "pnm_bin.cuh", "pnm_post.cuh", "pnm_fit.cuh", "pnm_profile.cuh",
+           os.path.join("..", "..", "include", "pnm_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -52,6 +53,24 @@ def build(force=False, verbose=False):
         print(proc.stdout)
     os.replace(LIB + ".tmp", LIB)
     return LIB
+
+
+DEMO_SRC = os.path.join(os.path.dirname(PKG), "examples", "abi_demo.cpp")
+DEMO_BIN = os.path.join(os.path.dirname(PKG), "examples", "abi_demo")
+
+
+def build_demo(force=False):
+    """examples/abi_demo: a compiled host on the C ABI alone (no Python, no torch), linked against the
+    in-tree library with an $ORIGIN-relative rpath so that it runs from the repository snapshot."""
+    build()
+    if not force and os.path.isfile(DEMO_BIN) and os.path.getmtime(DEMO_BIN) > max(os.path.getmtime(DEMO_SRC), os.path.getmtime(LIB)):
+        return DEMO_BIN
+    cmd = [find_nvcc(), "-std=c++17", "-O2", "-Wno-deprecated-gpu-targets", "-I", os.path.join(os.path.dirname(PKG), "include"),
+           DEMO_SRC, "-o", DEMO_BIN, "-L", PKG, "-lpnm_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../pynmap_b200"]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), proc.stdout))
+    return DEMO_BIN
 
 
 if __name__ == "__main__":
