@@ -363,10 +363,12 @@ def run_b200(args):
             "metric": METRIC, "value": n_local * n_gpus * args.steps / (total_ms * 1e-3), "unit": "particles/s",
             "n_gpus": n_gpus, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 particles, f64 accumulators" if args.accumulate == "f64" else "f32 particles, int64 fixed-point accumulators",
+            "dtype": "f32",          # particles, rotation and weighted terms in float32 (as in the reference); sums: see config
             "data": "synthetic",
             "config": {"workload": workload_name(n_gpus, n_local), "particles_per_gpu": n_local, "nXY": NXY, "nV": NV,
-                       "accumulate": args.accumulate, "parallelism": "particle shards x%d + NCCL reduce of partial grids (owner rank = step %% N)" % n_gpus
+                       "accumulate": args.accumulate,
+                       "accumulators": "float64 (L2 reductions)" if args.accumulate == "f64" else "int64 fixed point (bit-exact, order independent)",
+                       "parallelism": "particle shards x%d + NCCL reduce of partial grids (owner rank = step %% N)" % n_gpus
                        if n_gpus > 1 else "1 GPU",
                        "l2": "inputs (2.8 GB per GPU) are 22x larger than L2, no flush needed",
                        "streams": "scatter on the main stream; fold / reduce / finalise / smooth on a post-processing "
