@@ -33,7 +33,7 @@ PA, INCL = 30.0, 60.0
 SMOOTH_FWHM = (1.0, 1.0)
 BYTES_PER_PARTICLE = 28          # x y z vx vy vz w, float32
 SEED = 1234 + 1                  # base seed + config index
-CPU_SAMPLE = 4_000_000
+CPU_SAMPLE = int(os.environ.get("PNM_CPU_SAMPLE", 4_000_000))   # particles of the bounded CPU sample
 METRIC = "particles/s binned to maps+LOSVD cube"
 
 

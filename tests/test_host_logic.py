@@ -59,3 +59,29 @@ def test_result_dtype_follows_numpy():
     assert engine.result_dtype(f32, f64) == torch.float64 and engine.result_dtype(i64) == torch.float64
     assert engine.result_dtype(torch.zeros(2), None) == torch.float32
     assert engine.result_dtype(torch.zeros(2, dtype=torch.float64)) == torch.float64
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm) prints ONE JSON line with the contract's keys; a small
+    sample keeps this a few seconds.  Ranks other than 0 print nothing and exit 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PNM_CPU_SAMPLE="100000")
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"]
+    out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["n_gpus"] == 2 and j["unit"] == "particles/s" and j["value"] > 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1 and "workload" in j["config"]
+    assert j["e2e"]["value"] == j["value"] and j["e2e"]["h2d_bytes_per_step"] == 0
+    other = subprocess.run(cmd, env=dict(env, RANK="1", WORLD_SIZE="2"), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           text=True, timeout=600)
+    assert other.returncode == 0 and other.stdout.strip() == ""
