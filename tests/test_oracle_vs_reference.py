@@ -142,3 +142,43 @@ def test_ssp_tables_are_found_and_read_like_the_reference(ref, golden, monkeypat
     assert np.allclose(ml, g["node_ML"], rtol=1e-15, atol=0)
     monkeypatch.delenv("PNM_SSP_DIR")
     assert ssp.default_ssp_dir() == libdir          # the reference package is importable here (refshim put it on sys.path)
+
+
+def test_call_surface_matches_the_reference(ref):
+    """Drop-in check: every reference parameter exists here with the same name, position and default;
+    additions are keyword parameters appended after the reference's (accumulate=, on_error=, ...)."""
+    import inspect
+    import pynmap_b200 as mine
+
+    def params(fn):
+        return [(p.name, p.default if p.default is not inspect.Parameter.empty else "<required>", p.kind)
+                for p in inspect.signature(fn).parameters.values()]
+
+    def norm(v):
+        return v.tolist() if isinstance(v, np.ndarray) else v
+
+    pairs = [
+        (ref.rotation.rotate_mat, mine.rotation.rotate_mat), (ref.rotation.rotateXYZ_mat, mine.rotation.rotateXYZ_mat),
+        (ref.grid.points_2vmaps, mine.grid.points_2vmaps), (ref.grid.points_2map, mine.grid.points_2map),
+        (ref.grid.points_2losvds, mine.grid.points_2losvds), (ref.grid.point_2vprofiles, mine.grid.point_2vprofiles),
+        (ref.losvd.LOSVD.__init__, mine.LOSVD.__init__), (ref.losvd.LOSVD.convolve_spatial, mine.LOSVD.convolve_spatial),
+        (ref.losvd.LOSVD.rebin_spatial, mine.LOSVD.rebin_spatial), (ref.losvd.LOSVD.vmoments, mine.LOSVD.vmoments),
+        (ref.losvd.LOSVD.fitlosvd, mine.LOSVD.fitlosvd), (ref.fit_losvd.fitgh, mine.fit_losvd.fitgh),
+        (ref.misc_functions.gausshermite, mine.fit_losvd.gausshermite), (ref.misc_io.spread_amr, mine.amr.spread_amr),
+        (ref.pynmap.snapshot.__init__, mine.snapshot.__init__), (ref.pynmap.snapshot.rotate, mine.snapshot.rotate),
+        (ref.pynmap.snapshot.velocity_moments, mine.snapshot.velocity_moments),
+        (ref.pynmap.snapshot.create_map, mine.snapshot.create_map),
+        (ref.pynmap.snapshot.create_losvds, mine.snapshot.create_losvds),
+        (ref.pynmap.snapshot.amr_velocity_moments, mine.snapshot.amr_velocity_moments),
+        (ref.pynmap.snapshot.get_tensor_profiles, mine.snapshot.get_tensor_profiles),
+        (ref.pynmap.SnapMap.__init__, mine.SnapMap.__init__),
+    ]
+    for theirs, ours in pairs:
+        want, got = params(theirs), params(ours)
+        fixed = [p for p in want if p[2] not in (inspect.Parameter.VAR_KEYWORD, inspect.Parameter.VAR_POSITIONAL)]
+        assert len(got) >= len(fixed), (ours.__qualname__, got, want)
+        for k, (name, default, kind) in enumerate(fixed):
+            assert got[k][0] == name, (ours.__qualname__, k, got[k][0], name)
+            assert norm(got[k][1]) == norm(default), (ours.__qualname__, name, got[k][1], default)
+        extra = [p for p in got[len(fixed):] if p[2] not in (inspect.Parameter.VAR_KEYWORD, inspect.Parameter.VAR_POSITIONAL)]
+        assert all(p[1] != "<required>" for p in extra), (ours.__qualname__, extra)
