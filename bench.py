@@ -376,7 +376,12 @@ def run_b200(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "k_project_bin", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": BYTES_PER_PARTICLE * n_local,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                         # the unit that actually bounds the scatter: L2 accepts ~1.87e11 reduction
+                         # operations/s chip-wide (profiles/r01_micro_tma_mix.log); per particle 1 cube RED + 5/8 x 2 map
+                         # REDs + 3/8 x 1 TMA bulk reduction
+                         "reduction_ops": {"per_particle": 2.625, "achieved_per_s": 2.625 * n_local / (kernel_ms * 1e-3),
+                                           "peak_per_s": 1.87e11, "frac": 2.625 * n_local / (kernel_ms * 1e-3) / 1.87e11}},
             "cpu_baseline": base,
             "e2e": e2e,
             # our kernels launched by rank 0 inside the timed region: k_project_bin (+ k_fold_maps when
