@@ -384,8 +384,11 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
     if (VECLOAD) {
         const int64_t nvec = p.n / VN;
         int parity = 0;
-        for (int64_t i = tid; i < nvec; i += nthreads) {
-            T x[VN], y[VN], z[VN], vx[VN], vy[VN], vz[VN], w[VN];
+        // Rotated loop: the loads of the NEXT tile are issued after the current tile's particles have been
+        // consumed (their registers are free again) and BEFORE the TMA hand-off, so that the load latency runs
+        // under the bulk-reduction burst and the group wait instead of after them.
+        T x[VN], y[VN], z[VN], vx[VN], vy[VN], vz[VN], w[VN];
+        auto load_tile = [&](int64_t i) {
             Pack<T>::load(X + i * VN, x);
             Pack<T>::load(Y + i * VN, y);
             Pack<T>::load(VX + i * VN, vx);
@@ -395,6 +398,10 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
                 Pack<T>::load(VZ + i * VN, vz);
             }
             if (W) Pack<T>::load(W + i * VN, w);
+        };
+        int64_t i = tid;
+        if (i < nvec) load_tile(i);
+        while (i < nvec) {
             if (st.cap) {                                   // the stage used two tiles ago must have been read
                 tma_wait_read_1();
                 st.vals = stage_vals + ((size_t)parity * p.tma_slots * blockDim.x + threadIdx.x) * 4;
@@ -407,6 +414,8 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
                 one(i * VN + k, x[k], y[k], FUSED ? z[k] : (T)0, vx[k], FUSED ? vy[k] : (T)0, FUSED ? vz[k] : (T)0,
                     W ? w[k] : (T)1, run);
             run.flush(maps0, B.sums(), st);
+            i += nthreads;
+            if (i < nvec) load_tile(i);
             st.drain(maps0);
         }
         done = nvec * VN;
