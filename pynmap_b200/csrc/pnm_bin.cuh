@@ -31,6 +31,9 @@
 //     guess plus the deviation of np.linspace edges from an affine grid, computed at grid
 //     creation); only the ~2*eps fraction of near-edge particles consults the edge table.
 #pragma once
+#ifndef PNM_PAIRED
+#define PNM_PAIRED 1     // lane pairs share the (S1, S2) reductions of a pixel (MapRun::flush_paired); 0: one lane, one pixel
+#endif
 #include "pnm_common.cuh"
 
 namespace pnm {
@@ -211,6 +214,44 @@ struct MapRun {
         }
         off = -1;
     }
+    // Warp-synchronous flush (all 32 lanes call it together, a lane without a pending run passes off < 0).
+    // L2 takes one request per distinct 32-byte sector of a RED instruction, not per lane
+    // (scripts/red_pair_bench.cu: 1.8e11 lane-reductions/s with one lane per sector, 3.6e11 with two), and the
+    // (S1, S2) slots of a pixel share a sector.  Lanes 2j and 2j+1 therefore swap one value: the first RED of
+    // the pair carries S1 and S2 of the even lane's pixel, the second those of the odd lane's pixel -- two
+    // instructions as before, half the requests.
+    __device__ __forceinline__ void flush_paired(A* maps, int sums, TmaStage<ACC>& st, int lane) {
+        const bool with0 = (sums & PNM_SUM_W) && has0 && off >= 0;
+        bool valid = off >= 0;
+        const bool both = (sums & PNM_SUM_WD) && (sums & PNM_SUM_WD2);  // else the unused slot just receives zeros / unread sums
+        if (valid && both && st.push(off, s1, s2, s0, with0)) valid = false;
+        else if (with0) red_add(maps + off + kSlotS0, s0);
+        const bool odd = lane & 1;
+        const int my_off = valid ? off : -1;
+        const int x_off = __shfl_xor_sync(0xffffffffu, my_off, 1);
+        const A x_val = __shfl_xor_sync(0xffffffffu, odd ? s1 : s2, 1);     // the partner issues this lane's other half
+        {   // the even lane's pixel
+            const int o = odd ? x_off : my_off;
+            if (o >= 0) red_add(maps + o + (odd ? kSlotS2 : kSlotS1), odd ? x_val : s1);
+        }
+        {   // the odd lane's pixel
+            const int o = odd ? my_off : x_off;
+            if (o >= 0) red_add(maps + o + (odd ? kSlotS2 : kSlotS1), odd ? s2 : x_val);
+        }
+        off = -1;
+    }
+    // add one contribution; returns true when the pixel changed, i.e. the previous run (moved to `prev`) is due
+    __device__ __forceinline__ bool add_deferred(MapRun& prev, int o, bool use0, A a0, A a1, A a2) {
+        bool due = false;
+        if (o != off) {
+            prev = *this; due = prev.off >= 0;
+            off = o; s0 = 0; s1 = a1; s2 = a2; has0 = false;
+        } else {
+            s1 += a1; s2 += a2;
+        }
+        if (use0) { s0 += a0; has0 = true; }
+        return due;
+    }
     __device__ __forceinline__ void add(A* maps, int sums, TmaStage<ACC>& st, int o, bool use0, A a0, A a1, A a2) {
         if (o != off) {
             flush(maps, sums, st);
@@ -242,7 +283,8 @@ struct Binner {
 
     // (px, py, d) already projected: locate the bins, then reduce
     __device__ __forceinline__ void scatter(A* maps, A* cube, MapRun<ACC>& run, TmaStage<ACC>& st,
-                                            T px, T py, T d, T w, bool masked_in) {
+                                            T px, T py, T d, T w, bool masked_in,
+                                            MapRun<ACC>* prev = nullptr, bool* due = nullptr) {
         if (masked_in) {
             if (mask_mode == PNM_MASK_PLAIN) return;
             if (mask_mode == PNM_MASK_AND_NONFINITE && !is_finite(d)) return;
@@ -270,8 +312,11 @@ struct Binner {
                     wdd = (T)__fmul_rn((float)w, (float)dd);
                 } else { wd = mul_rn(w, d); wdd = mul_rn(w, dd); }
             } else { wd = mul_rn(w, d); wdd = mul_rn(w, dd); }
-            run.add(maps, sm, st, (iy * nx + ix) * PNM_MAP_SLOTS, use0, to_acc<ACC>(w, sc0),
-                    to_acc<ACC>(wd, sc1), to_acc<ACC>(wdd, sc2));
+            const int off = (iy * nx + ix) * PNM_MAP_SLOTS;
+            if (PNM_PAIRED && due)                              // paired mode: a finished run goes back to the caller
+                *due = run.add_deferred(*prev, off, use0, to_acc<ACC>(w, sc0), to_acc<ACC>(wd, sc1), to_acc<ACC>(wdd, sc2));
+            else
+                run.add(maps, sm, st, off, use0, to_acc<ACC>(w, sc0), to_acc<ACC>(wd, sc1), to_acc<ACC>(wdd, sc2));
         }
         if (in_v) red_add(cube + (iv * npix + ix * ny + iy), to_acc<ACC>(w, sc0));
     }
@@ -399,7 +444,44 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
             }
             if (W) Pack<T>::load(W + i * VN, w);
         };
-        int64_t i = tid;
+        if (PNM_PAIRED && SIMPLE) {
+            // warp-uniform trip count: the paired flush is warp-synchronous; lanes past the end pass empty runs
+            const int lane = threadIdx.x & 31;
+            int64_t ib = tid - lane;
+            bool live = ib + lane < nvec;
+            if (live) load_tile(ib + lane);
+            while (ib < nvec) {
+                if (st.cap) {
+                    tma_wait_read_1();
+                    st.vals = stage_vals + ((size_t)parity * p.tma_slots * blockDim.x + threadIdx.x) * 4;
+                    st.offs = stage_offs + (size_t)parity * p.tma_slots * blockDim.x + threadIdx.x;
+                    parity ^= 1;
+                }
+                MapRun<ACC> run;
+#pragma unroll
+                for (int k = 0; k < VN; ++k) {
+                    MapRun<ACC> prev;
+                    bool due = false;
+                    if (live) {
+                        T px = x[k], py = y[k], d = vx[k];
+                        if (FUSED) {
+                            px = rot_row(m[0], m[1], m[2], x[k], y[k], z[k]);
+                            py = rot_row(m[3], m[4], m[5], x[k], y[k], z[k]);
+                            d = rot_row(m[6], m[7], m[8], vx[k], vy[k], vz[k]);
+                        }
+                        B.scatter(maps0, cube0, run, st, px, py, d, W ? w[k] : (T)1, false, &prev, &due);
+                    }
+                    if (!due) prev.off = -1;
+                    prev.flush_paired(maps0, B.sums(), st, lane);
+                }
+                run.flush_paired(maps0, B.sums(), st, lane);
+                ib += nthreads;
+                live = ib + lane < nvec;
+                if (live) load_tile(ib + lane);
+                st.drain(maps0);
+            }
+        }
+        int64_t i = (PNM_PAIRED && SIMPLE) ? nvec : tid;
         if (i < nvec) load_tile(i);
         while (i < nvec) {
             if (st.cap) {                                   // the stage used two tiles ago must have been read
