@@ -14,7 +14,11 @@ KEEP = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__occupancy_limit_registers",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "sm__cycles_elapsed.avg", "sm__inst_executed_pipe_lsu.sum",
-        "smsp__inst_executed_op_global_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum")
+        "smsp__inst_executed_op_global_red.sum", "l1tex__t_set_accesses_pipe_lsu_mem_global_op_red.sum",
+        "lts__t_requests.sum", "lts__t_requests_srcunit_tex.sum", "lts__t_requests_srcunit_ltcfabric.sum",
+        "lts__t_requests_srcunit_tex_op_read.sum", "lts__t_requests_srcunit_tex_op_red.sum", "lts__cycles_active.sum",
+        "lts__d_atomic_input_cycles_active.avg.pct_of_peak_sustained_elapsed",
+        "lts__d_atomic_input_cycles_active.max.pct_of_peak_sustained_elapsed")
 
 
 def main():
