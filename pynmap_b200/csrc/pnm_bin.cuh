@@ -7,9 +7,10 @@
 // rotation.py:115-117 (rotation), grid.py:121-131 / :200-201 (2-D moment histograms),
 // grid.py:252-259 (3-D histogram).
 //
-// Roofline: HBM (28 B per float32 particle).  What actually bounds the kernel is the SM's
-// reduction-issue rate (0.77 scattered RED lanes per clock per SM, measured), so the design
-// minimises REDs per particle, keeps the instruction stream short and spreads same-address traffic:
+// Roofline: HBM (28 B per float32 particle).  What actually bounds the kernel is the rate at which L2
+// accepts reduction REQUESTS: one per distinct 32-byte sector of a RED instruction (~1.9e11/s chip-wide,
+// scripts/red_pair_bench.cu), shared with the particle stream.  The design therefore minimises requests
+// per particle, keeps the instruction stream short and spreads same-address traffic:
 //   * accumulators (<= 66 MB for 128x128x256) stay resident in the 126 MB L2; the particle stream
 //     is loaded with 256-bit LDG, no L1 allocation and an L2 evict-first policy;
 //   * maps are replicated R times (one replica per warp id) so that the galaxy-centre pixels, which
@@ -19,13 +20,14 @@
 //   * consecutive particles of a thread that fall in the same pixel are merged in registers before
 //     the reduction (free for random order, ~1 per run for space-filling-curve ordered snapshots);
 //   * with PNM_W_FROM_CUBE the map's sum w costs no RED at all for particles inside the V range;
-//   * HYBRID SCATTER: (sum w*d, sum w*d*d[, sum w]) sit in one 32-byte sector, so part of the map
-//     updates (3-4 of a tile's 8) are staged in shared memory and sent as ONE 16- or 32-byte TMA
-//     bulk reduction (cp.reduce.async.bulk.global.shared::cta ... add.f64/.u64, SASS UBLKRED)
-//     instead of two or three LSU REDs.  The TMA unit sustains ~7.5e10 such ops/s per GPU next to
-//     the LSU's 1.9e11 REDs/s and the two overlap (scripts/tma_mix_bench.cu).  UBLKRED is a
-//     warp-uniform instruction: per-lane destinations cost an ELECT/R2UR issue loop, which is why
-//     the share is 3-4 of 8 and not more (measured, see pnm_api.cu);
+//   * LANE PAIRS: (sum w*d, sum w*d*d) of a pixel sit in one sector, so lanes 2j / 2j+1 swap one value
+//     (3 SHFL) and every RED instruction carries BOTH moments of one pixel in adjacent lanes: two
+//     instructions as before, half the L2 requests (MapRun::flush_paired).  Per particle: one request
+//     for the cube voxel, one for the pixel;
+//   * TMA BULK REDUCTIONS for maps without a cube: a 32-byte record (sum w*d, sum w*d*d, sum w, -) staged
+//     in shared memory goes out as ONE cp.reduce.async.bulk.global.shared::cta ... add.f64/.u64 (SASS
+//     UBLKRED) and also carries sum w; 2 of a tile's 8 updates take this path (the TMA unit sustains
+//     ~7.5e10 such operations/s).  With the cube the paired REDs leave it nothing to save;
 //   * bin lookup: the uniform guess floor((x-x0)*inv) is PROVABLY the numpy bin whenever its
 //     fractional part is further than `eps` from an integer (eps bounds the float rounding of the
 //     guess plus the deviation of np.linspace edges from an affine grid, computed at grid
@@ -143,9 +145,8 @@ __device__ __forceinline__ void red_add(long long* p, long long v) {
 // (S1, S2, S0, pad; consecutive threads, consecutive records) + the matching destination offsets.  A thread
 // only ever touches its own records, so ordering needs no CTA barrier: generic-proxy writes ->
 // fence.proxy.async -> bulk reductions -> commit_group; before a stage is rewritten two tiles
-// later, wait_group.read 1 guarantees the TMA unit has read it.
-// of the (up to) 8 map updates of a tile; the rest take the LSU path.  Measured on the bench
-// workload (1e8 particles, maps + cube): 0 -> 1.78 ms, 2 -> 1.65, 4 -> 1.59, 5 -> 1.67, 6 -> 1.82
+// later, wait_group.read 1 guarantees the TMA unit has read it.  BinParams::tma_slots of the (up to) 8
+// map updates of a tile go this way; the rest take the (lane-paired) LSU path.
 constexpr int kTmaSlots = 6;      // upper bound; the launcher picks how many are used (BinParams::tma_slots)
 constexpr int kTmaStages = 2;
 
@@ -363,7 +364,7 @@ __host__ __device__ inline size_t bin_stage_bytes(int threads, int slots) {
 // ---- kernel: persistent grid-stride loop; each thread takes Pack<T>::N consecutive particles per
 // array with one 256-bit load (VECLOAD), scalar path for the tail and for unaligned pointers.
 // SIMPLE = one view, one matrix, no mask: the matrix lives in registers, consecutive particles of a
-// thread merge their map contributions and the hybrid LSU/TMA scatter is active. ----------------
+// thread merge their map contributions, lane pairs share the map reductions and the TMA path is available. --
 template <typename T, bool FUSED, int ACC, bool VECLOAD, bool SIMPLE, int SUMS>
 __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(const __grid_constant__ BinParams p) {
     using A = typename AccT<ACC>::type;
