@@ -292,11 +292,11 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     p.rep_shift = env_int("PNM_REP_SHIFT", 5);
     // hybrid scatter: 16-byte TMA bulk reductions need a 16-byte aligned maps accumulator
     p.tma_slots = (acc_maps && (reinterpret_cast<uintptr_t>(acc_maps) & 15) == 0 && (sums & PNM_SUM_WD) && (sums & PNM_SUM_WD2))
-                      ? std::max(0, std::min(env_int("PNM_TMA_SLOTS", (sums & PNM_W_FROM_CUBE) ? 0 : 2), pnm::kTmaSlots)) : 0;
-    // (measured with lane-paired reductions, 1e8 particles: maps + cube 1.28 / 1.30 / 1.38 / 1.53 ms for 0 / 2 / 3 / 4 of a
-    //  tile's 8 updates through the TMA unit -- a paired (S1, S2) reduction is one L2 request, like a bulk reduction, so
-    //  the TMA unit has nothing left to save; maps only, where a 32-byte record also carries S0: 1.28 / 1.22 / 1.17 /
-    //  1.20 / 1.35 ms for 0 / 1 / 2 / 3 / 4)
+                      ? std::max(0, std::min(env_int("PNM_TMA_SLOTS", 0), pnm::kTmaSlots)) : 0;
+    // (measured with lane-paired / lane-quad reductions, 1e8 particles: maps + cube 1.28 / 1.30 / 1.38 / 1.53 ms for
+    //  0 / 2 / 3 / 4 of a tile's 8 updates through the TMA unit; maps only 0.86 / 0.88 ms for 0 / 2 -- a paired or quad
+    //  reduction is one L2 request per pixel, like a bulk reduction, so the TMA unit has nothing left to save and the
+    //  path is off unless PNM_TMA_SLOTS asks for it)
     for (int k = 0; k < 3; ++k) p.scale[k] = (acc_mode == PNM_ACC_FIXED) ? scales3_host[k] : 1.0;
     p.acc_maps = acc_maps; p.acc_cube = acc_cube;
     p.maps_stride = pnm_maps_acc_elems(g); p.cube_stride = pnm_cube_acc_elems(g);

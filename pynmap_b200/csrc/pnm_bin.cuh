@@ -241,6 +241,39 @@ struct MapRun {
         }
         off = -1;
     }
+    // Same idea for runs that carry sum w with every pixel (no cube to recover it from): the three sums of a
+    // pixel share a sector, so a quad of lanes transposes its 4 x (S1, S2, S0, -) values (two butterfly stages)
+    // and issues four REDs, each carrying all three sums of ONE pixel in lanes q = 0, 1, 2 of the quad (lane 3
+    // idles): one L2 request per pixel instead of two or three.  Slot index == lane-in-quad by construction.
+    __device__ __forceinline__ void flush_quad(A* maps, int sums, int lane) {
+        static_assert(kSlotS1 == 0 && kSlotS2 == 1 && kSlotS0 == 2, "slot order is the lane order of the quad");
+        const int q = lane & 3;
+        A a0 = s1, a1 = s2, a2 = has0 ? s0 : A(0), a3 = A(0);
+        {   // stage 1: partner lane ^ 1 -- even lanes keep (0, 2) and receive (1, 3), odd lanes the other way round
+            const bool odd = q & 1;
+            A x = odd ? a0 : a1, y = odd ? a2 : a3;
+            x = __shfl_xor_sync(0xffffffffu, x, 1); y = __shfl_xor_sync(0xffffffffu, y, 1);
+            if (odd) { a0 = x; a2 = y; } else { a1 = x; a3 = y; }
+        }
+        {   // stage 2: partner lane ^ 2
+            const bool hi = q & 2;
+            A x = hi ? a0 : a2, y = hi ? a1 : a3;
+            x = __shfl_xor_sync(0xffffffffu, x, 2); y = __shfl_xor_sync(0xffffffffu, y, 2);
+            if (hi) { a0 = x; a1 = y; } else { a2 = x; a3 = y; }
+        }
+        // lane q now holds sum #q of the quad's four pixels: a_i = (sum q of the pixel of lane i)
+        const int base = lane & ~3;
+        const int o0 = __shfl_sync(0xffffffffu, off, base), o1 = __shfl_sync(0xffffffffu, off, base + 1);
+        const int o2 = __shfl_sync(0xffffffffu, off, base + 2), o3 = __shfl_sync(0xffffffffu, off, base + 3);
+        const bool mine = q == 0 ? (sums & PNM_SUM_WD) != 0 : q == 1 ? (sums & PNM_SUM_WD2) != 0 : q == 2 ? (sums & PNM_SUM_W) != 0 : false;
+        if (mine) {
+            if (o0 >= 0) red_add(maps + o0 + q, a0);
+            if (o1 >= 0) red_add(maps + o1 + q, a1);
+            if (o2 >= 0) red_add(maps + o2 + q, a2);
+            if (o3 >= 0) red_add(maps + o3 + q, a3);
+        }
+        off = -1;
+    }
     // add one contribution; returns true when the pixel changed, i.e. the previous run (moved to `prev`) is due
     __device__ __forceinline__ bool add_deferred(MapRun& prev, int o, bool use0, A a0, A a1, A a2) {
         bool due = false;
@@ -448,6 +481,8 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
         if (PNM_PAIRED && SIMPLE) {
             // warp-uniform trip count: the paired flush is warp-synchronous; lanes past the end pass empty runs
             const int lane = threadIdx.x & 31;
+            // sum w travels with every pixel (no cube to recover it from) -> quads, else pairs
+            const bool quad = (B.sums() & PNM_SUM_W) && !(B.sums() & PNM_W_FROM_CUBE);
             int64_t ib = tid - lane;
             bool live = ib + lane < nvec;
             if (live) load_tile(ib + lane);
@@ -473,9 +508,9 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
                         B.scatter(maps0, cube0, run, st, px, py, d, W ? w[k] : (T)1, false, &prev, &due);
                     }
                     if (!due) prev.off = -1;
-                    prev.flush_paired(maps0, B.sums(), st, lane);
+                    if (quad) prev.flush_quad(maps0, B.sums(), lane); else prev.flush_paired(maps0, B.sums(), st, lane);
                 }
-                run.flush_paired(maps0, B.sums(), st, lane);
+                if (quad) run.flush_quad(maps0, B.sums(), lane); else run.flush_paired(maps0, B.sums(), st, lane);
                 ib += nthreads;
                 live = ib + lane < nvec;
                 if (live) load_tile(ib + lane);
