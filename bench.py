@@ -379,10 +379,10 @@ def run_b200(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          # the unit that actually bounds the scatter: L2 takes one request per
                          # distinct 32-byte sector of a reduction instruction, ~1.87e11 scattered requests/s chip-wide
-                         # (scripts/red_pair_bench.cu, profiles/r01_micro_tma_mix.log); per particle: 1 cube RED + 1 request
-                         # for the lane-paired (S1, S2) REDs
-                         "l2_reduction_requests": {"per_particle": 2.0, "achieved_per_s": 2.0 * n_local / (kernel_ms * 1e-3),
-                                                   "peak_per_s": 1.87e11, "frac": 2.0 * n_local / (kernel_ms * 1e-3) / 1.87e11}},
+                         # (scripts/red_pair_bench.cu, profiles/r01_micro_tma_mix.log); with the interleaved cube all
+                         # three sums of a particle share a sector: one request per particle
+                         "l2_reduction_requests": {"per_particle": 1.0, "achieved_per_s": 1.0 * n_local / (kernel_ms * 1e-3),
+                                                   "peak_per_s": 1.87e11, "frac": 1.0 * n_local / (kernel_ms * 1e-3) / 1.87e11}},
             "cpu_baseline": base,
             "e2e": e2e,
             # our kernels launched by rank 0 inside the timed region: k_project_bin (+ k_fold_maps when

@@ -75,18 +75,18 @@ int main() {
         CU(cudaMalloc(&d[k], n * sizeof(float)));
         CU(cudaMemcpy(d[k], h[k].data(), n * sizeof(float), cudaMemcpyHostToDevice));
     }
-    const int64_t me = pnm_maps_acc_elems(g), ce = pnm_cube_acc_elems(g);
+    const int64_t me = pnm_maps_acc_elems(g), ce = pnm_cube_acc_elems(g), cme = pnm_cube_moments_acc_elems(g);
     double *acc_maps, *acc_cube, *M, *V, *S, *cube, *smooth, *work;
     CU(cudaMalloc(&acc_maps, me * 8)); CU(cudaMemset(acc_maps, 0, me * 8));
-    CU(cudaMalloc(&acc_cube, ce * 8)); CU(cudaMemset(acc_cube, 0, ce * 8));
+    CU(cudaMalloc(&acc_cube, cme * 8)); CU(cudaMemset(acc_cube, 0, cme * 8));   // interleaved cube: w per voxel + the moments
     CU(cudaMalloc(&M, nx * ny * 8)); CU(cudaMalloc(&V, nx * ny * 8)); CU(cudaMalloc(&S, nx * ny * 8));
     CU(cudaMalloc(&cube, ce * 8)); CU(cudaMalloc(&smooth, ce * 8)); CU(cudaMalloc(&work, ce * 8));
 
-    const int sums = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2 | PNM_SUM_CUBE | PNM_W_FROM_CUBE;
+    const int sums = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2 | PNM_SUM_CUBE | PNM_W_FROM_CUBE | PNM_CUBE_MOMENTS;
     CK(pnm_project_bin(g, n, PNM_F32, d[0], d[1], d[2], d[3], d[4], d[5], d[6], nullptr, PNM_MASK_NONE, mat, 1, 1, sums,
                        PNM_ACC_F64, nullptr, acc_maps, acc_cube, nullptr));
     CK(pnm_finalize_vmaps(g, acc_maps, acc_cube, sums, PNM_ACC_F64, nullptr, M, V, S, nullptr, nullptr, nullptr));
-    CK(pnm_finalize_cube(g, acc_cube, PNM_ACC_F64, 1.0, cube, nullptr));
+    CK(pnm_finalize_cube(g, acc_cube, sums, PNM_ACC_F64, 1.0, cube, nullptr));
     const double taps[5] = {0.06136, 0.24477, 0.38774, 0.24477, 0.06136};
     CK(pnm_smooth_cube(cube, smooth, work, nx, ny, nv, taps, 5, taps, 5, nullptr));
     CU(cudaDeviceSynchronize());

@@ -70,6 +70,12 @@ extern "C" {
  * directly: particles inside the V range go to the cube only, the others to maps slot 0,
  * and pnm_finalize_vmaps adds the cube's V-sum back.  One atomic fewer per particle.       */
 #define PNM_W_FROM_CUBE 16
+/* With PNM_W_FROM_CUBE: the cube accumulator uses the INTERLEAVED layout [ceil(nv/2)][ix][iy][4] =
+ * { w of velocity bin 2g, w of bin 2g+1, sum w*d, sum w*d*d } (pnm_cube_moments_acc_elems elements), so that all
+ * three sums of a particle inside the V range fall into one 32-byte sector -- one L2 request per particle.  The maps
+ * accumulator then only receives the particles outside the V range; pnm_finalize_vmaps / pnm_finalize_cube take the
+ * same flag.                                                                                        */
+#define PNM_CUBE_MOMENTS 256
 /* Mixed input dtypes (pnm_bin_points with dtype = PNM_F64 only).  numpy evaluates `wm * vm` and
  * `wm * vm**2` (grid.py:128-131, :201) in the result type of the two operands, which is float32 when
  * both are float32 even if the coordinates are float64.  Arrays are still passed as float64:
@@ -120,6 +126,7 @@ int pnm_grid_destroy(pnm_grid* g);
  * at finalisation, the cube accumulator is velocity-major.  Sizes per view, in 8-byte elements:  */
 int64_t pnm_maps_acc_elems(const pnm_grid* g); /* replicas*ny*nx*PNM_MAP_SLOTS */
 int64_t pnm_cube_acc_elems(const pnm_grid* g); /* nx*ny*nv                     */
+int64_t pnm_cube_moments_acc_elems(const pnm_grid* g); /* ceil(nv/2)*nx*ny*4 with PNM_CUBE_MOMENTS */
 int pnm_grid_map_replicas(const pnm_grid* g);
 /* Sums the map replicas into the first one, so that a multi-GPU reduction only has to move the
  * first ny*nx*PNM_MAP_SLOTS elements.  clear_others != 0 also zeroes replicas 1.. (the buffer can
@@ -163,7 +170,7 @@ int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_
 int pnm_finalize_map(const pnm_grid* g, const void* acc_maps, int acc_mode,
                      const double* scales3_host, double* W, double* D, double* DW, void* stream);
 /* cube accumulator -> float64 cube[ix][iy][iv] (the layout of np.histogramdd, grid.py:259); not in place */
-int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int acc_mode, double scale_w,
+int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int sums, int acc_mode, double scale_w,
                       double* cube_out, void* stream);
 
 /* ---- a5: separable Gaussian smoothing of every velocity slice (losvd.py:127-135) ------------

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("PNM_B200_LIB", os.path.join(_HERE, "libpnm_b200.so"))
 # constants mirrored from include/pnm_b200.h
 F32, F64 = 0, 1
 ACC_F64, ACC_FIXED = 0, 1
-SUM_W, SUM_WD, SUM_WD2, SUM_CUBE, W_FROM_CUBE, MAPS_FOLDED, VAL_D32, VAL_W32 = 1, 2, 4, 8, 16, 32, 64, 128
+SUM_W, SUM_WD, SUM_WD2, SUM_CUBE, W_FROM_CUBE, MAPS_FOLDED, VAL_D32, VAL_W32, CUBE_MOMENTS = 1, 2, 4, 8, 16, 32, 64, 128, 256
 MASK_NONE, MASK_AND_NONFINITE, MASK_PLAIN = 0, 1, 2
 MAX_EDGES, MAX_CHAIN, MAX_VIEWS, MAX_TAPS, MAP_SLOTS = 4097, 8, 64, 255, 4
 MAX_MATS = 64
@@ -38,7 +38,8 @@ _SIGNATURES = {
                                POINTER(c_double), _P, _P, _P]),
     "pnm_finalize_vmaps": (c_int, [_P, _P, _P, c_int, c_int, POINTER(c_double), _P, _P, _P, _P, _P, _P]),
     "pnm_finalize_map": (c_int, [_P, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),
-    "pnm_finalize_cube": (c_int, [_P, _P, c_int, c_double, _P, _P]),
+    "pnm_finalize_cube": (c_int, [_P, _P, c_int, c_int, c_double, _P, _P]),
+    "pnm_cube_moments_acc_elems": (c_int64, [_P]),
     "pnm_smooth_cube": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, POINTER(c_double), c_int32,
                                 POINTER(c_double), c_int32, _P]),
     "pnm_cube_moments": (c_int, [_P, c_int32, c_int32, c_int32, _P, c_double, _P, _P, _P, _P]),

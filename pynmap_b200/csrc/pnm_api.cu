@@ -203,6 +203,7 @@ int pnm_grid_destroy(pnm_grid* g) {
 int64_t pnm_maps_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * PNM_MAP_SLOTS * g->replicas : 0; }
 int pnm_grid_map_replicas(const pnm_grid* g) { return g ? g->replicas : 0; }
 int64_t pnm_cube_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * g->nv : 0; }
+int64_t pnm_cube_moments_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * ((g->nv + 1) / 2) * 4 : 0; }
 
 }  // extern "C"
 
@@ -225,6 +226,7 @@ int launch_bin(const pnm::BinParams& p, int acc_mode, cudaStream_t st) {
     // hot configurations get the set of sums as a compile-time constant (fused path only)
     constexpr int kFull = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2 | PNM_SUM_CUBE | PNM_W_FROM_CUBE;
     constexpr int kMaps = PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2;
+    constexpr int kFullM = kFull | PNM_CUBE_MOMENTS;
 #define PNM_LAUNCH(ACC, VL, SIMPLE, SUMS)                                                            \
     do {                                                                                             \
         auto kern = pnm::k_project_bin<T, FUSED, ACC, VL, SIMPLE, SUMS>;                             \
@@ -234,7 +236,8 @@ int launch_bin(const pnm::BinParams& p, int acc_mode, cudaStream_t st) {
     } while (0)
 #define PNM_LAUNCH2(ACC)                                                                             \
     do {                                                                                             \
-        if (aligned && simple && FUSED && p.sums == kFull) PNM_LAUNCH(ACC, true, true, kFull);       \
+        if (aligned && simple && FUSED && p.sums == kFullM) PNM_LAUNCH(ACC, true, true, kFullM);     \
+        else if (aligned && simple && FUSED && p.sums == kFull) PNM_LAUNCH(ACC, true, true, kFull);  \
         else if (aligned && simple && FUSED && p.sums == kMaps) PNM_LAUNCH(ACC, true, true, kMaps);  \
         else if (aligned && simple && FUSED && p.sums == PNM_SUM_CUBE) PNM_LAUNCH(ACC, true, true, PNM_SUM_CUBE); \
         else if (aligned && simple) PNM_LAUNCH(ACC, true, true, -1);                                 \
@@ -263,6 +266,11 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     if ((sums & PNM_SUM_CUBE) && (!acc_cube || g->nv < 1)) return fail(PNM_EINVAL, "%s: cube requested without cube accumulator / V axis", who);
     if ((sums & PNM_W_FROM_CUBE) && !((sums & PNM_SUM_CUBE) && (sums & PNM_SUM_W)))
         return fail(PNM_EINVAL, "%s: PNM_W_FROM_CUBE needs PNM_SUM_W|PNM_SUM_CUBE", who);
+    if ((sums & PNM_CUBE_MOMENTS) &&
+        (sums & (PNM_W_FROM_CUBE | PNM_SUM_WD | PNM_SUM_WD2)) != (PNM_W_FROM_CUBE | PNM_SUM_WD | PNM_SUM_WD2))
+        return fail(PNM_EINVAL, "%s: PNM_CUBE_MOMENTS needs PNM_SUM_W|PNM_SUM_WD|PNM_SUM_WD2|PNM_SUM_CUBE|PNM_W_FROM_CUBE", who);
+    if ((sums & PNM_CUBE_MOMENTS) && (int64_t)g->nx * g->ny * ((g->nv + 1) / 2) * 4 >= (1LL << 31))
+        return fail(PNM_ELIMIT, "%s: interleaved cube of 2^31 elements or more", who);
     if ((sums & (PNM_VAL_D32 | PNM_VAL_W32)) && (fused || dtype != PNM_F64))
         return fail(PNM_EINVAL, "%s: PNM_VAL_D32 / PNM_VAL_W32 describe float32 values carried as float64 (pnm_bin_points, PNM_F64)", who);
     if (mask_mode != PNM_MASK_NONE && !mask) return fail(PNM_EINVAL, "%s: mask_mode without mask", who);
@@ -331,7 +339,7 @@ int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_
                        const double* scales3_host, double* M, double* V, double* S, double* S1, double* S2,
                        void* stream) {
     if (!g || !acc_maps) return fail(PNM_EINVAL, "pnm_finalize_vmaps: null grid / accumulator");
-    const int wfc = (sums & PNM_W_FROM_CUBE) ? 1 : 0;
+    const int wfc = (sums & PNM_CUBE_MOMENTS) ? 2 : (sums & PNM_W_FROM_CUBE) ? 1 : 0;
     if (wfc && !acc_cube) return fail(PNM_EINVAL, "pnm_finalize_vmaps: PNM_W_FROM_CUBE without cube");
     const int npix = g->nx * g->ny;
     const int grid = (npix + 31) / 32;
@@ -370,17 +378,18 @@ int pnm_finalize_map(const pnm_grid* g, const void* acc_maps, int acc_mode, cons
     return PNM_OK;
 }
 
-int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int acc_mode, double scale_w, double* cube_out,
+int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int sums, int acc_mode, double scale_w, double* cube_out,
                       void* stream) {
+    const int moments = (sums & PNM_CUBE_MOMENTS) ? 1 : 0;
     if (!g || !acc_cube || !cube_out) return fail(PNM_EINVAL, "pnm_finalize_cube: null argument");
     if (static_cast<const void*>(cube_out) == acc_cube) return fail(PNM_EINVAL, "pnm_finalize_cube: cannot run in place");
     if (g->nv < 1) return fail(PNM_EINVAL, "pnm_finalize_cube: grid has no V axis");
     const int npix = g->nx * g->ny;
     const dim3 grid((npix + 31) / 32, (g->nv + 31) / 32), block(32, 8);
     if (acc_mode == PNM_ACC_F64)
-        pnm::k_cube_out<PNM_ACC_F64><<<grid, block, 0, as_stream(stream)>>>(acc_cube, cube_out, npix, g->nv, 1.0);
+        pnm::k_cube_out<PNM_ACC_F64><<<grid, block, 0, as_stream(stream)>>>(acc_cube, cube_out, npix, g->nv, 1.0, moments);
     else if (acc_mode == PNM_ACC_FIXED)
-        pnm::k_cube_out<PNM_ACC_FIXED><<<grid, block, 0, as_stream(stream)>>>(acc_cube, cube_out, npix, g->nv, 1.0 / scale_w);
+        pnm::k_cube_out<PNM_ACC_FIXED><<<grid, block, 0, as_stream(stream)>>>(acc_cube, cube_out, npix, g->nv, 1.0 / scale_w, moments);
     else
         return fail(PNM_EINVAL, "pnm_finalize_cube: acc_mode %d", acc_mode);
     PNM_CUDA(cudaGetLastError());

@@ -196,6 +196,37 @@ struct TmaStage {
     }
 };
 
+// ---- lane quads ------------------------------------------------------------------------------------
+// Four lanes hold four records (off, a0..a3) whose values belong to ONE 32-byte sector each.  Two butterfly stages
+// transpose the 4 x 4 values, so that lane q of the quad holds value #q of all four records, and four REDs follow,
+// each carrying one record in the quad's four lanes: L2 sees one request per record (red_pair_bench: one request
+// per distinct sector of an instruction).  off < 0: no record.  `lanes`: bit q set = value #q is wanted.
+template <typename A>
+__device__ __forceinline__ void quad_reduce(A* base, int off, A a0, A a1, A a2, A a3, int lane, int lanes) {
+    const int q = lane & 3;
+    {   // stage 1: partner lane ^ 1 -- even lanes keep (0, 2) and receive (1, 3), odd lanes the other way round
+        const bool odd = q & 1;
+        A x = odd ? a0 : a1, y = odd ? a2 : a3;
+        x = __shfl_xor_sync(0xffffffffu, x, 1); y = __shfl_xor_sync(0xffffffffu, y, 1);
+        if (odd) { a0 = x; a2 = y; } else { a1 = x; a3 = y; }
+    }
+    {   // stage 2: partner lane ^ 2
+        const bool hi = q & 2;
+        A x = hi ? a0 : a2, y = hi ? a1 : a3;
+        x = __shfl_xor_sync(0xffffffffu, x, 2); y = __shfl_xor_sync(0xffffffffu, y, 2);
+        if (hi) { a0 = x; a1 = y; } else { a2 = x; a3 = y; }
+    }
+    const int qb = lane & ~3;
+    const int o0 = __shfl_sync(0xffffffffu, off, qb), o1 = __shfl_sync(0xffffffffu, off, qb + 1);
+    const int o2 = __shfl_sync(0xffffffffu, off, qb + 2), o3 = __shfl_sync(0xffffffffu, off, qb + 3);
+    if ((lanes >> q) & 1) {
+        if (o0 >= 0) red_add(base + o0 + q, a0);
+        if (o1 >= 0) red_add(base + o1 + q, a1);
+        if (o2 >= 0) red_add(base + o2 + q, a2);
+        if (o3 >= 0) red_add(base + o3 + q, a3);
+    }
+}
+
 // pending run of map contributions that share one pixel (merged in registers)
 template <int ACC>
 struct MapRun {
@@ -247,31 +278,8 @@ struct MapRun {
     // idles): one L2 request per pixel instead of two or three.  Slot index == lane-in-quad by construction.
     __device__ __forceinline__ void flush_quad(A* maps, int sums, int lane) {
         static_assert(kSlotS1 == 0 && kSlotS2 == 1 && kSlotS0 == 2, "slot order is the lane order of the quad");
-        const int q = lane & 3;
-        A a0 = s1, a1 = s2, a2 = has0 ? s0 : A(0), a3 = A(0);
-        {   // stage 1: partner lane ^ 1 -- even lanes keep (0, 2) and receive (1, 3), odd lanes the other way round
-            const bool odd = q & 1;
-            A x = odd ? a0 : a1, y = odd ? a2 : a3;
-            x = __shfl_xor_sync(0xffffffffu, x, 1); y = __shfl_xor_sync(0xffffffffu, y, 1);
-            if (odd) { a0 = x; a2 = y; } else { a1 = x; a3 = y; }
-        }
-        {   // stage 2: partner lane ^ 2
-            const bool hi = q & 2;
-            A x = hi ? a0 : a2, y = hi ? a1 : a3;
-            x = __shfl_xor_sync(0xffffffffu, x, 2); y = __shfl_xor_sync(0xffffffffu, y, 2);
-            if (hi) { a0 = x; a1 = y; } else { a2 = x; a3 = y; }
-        }
-        // lane q now holds sum #q of the quad's four pixels: a_i = (sum q of the pixel of lane i)
-        const int base = lane & ~3;
-        const int o0 = __shfl_sync(0xffffffffu, off, base), o1 = __shfl_sync(0xffffffffu, off, base + 1);
-        const int o2 = __shfl_sync(0xffffffffu, off, base + 2), o3 = __shfl_sync(0xffffffffu, off, base + 3);
-        const bool mine = q == 0 ? (sums & PNM_SUM_WD) != 0 : q == 1 ? (sums & PNM_SUM_WD2) != 0 : q == 2 ? (sums & PNM_SUM_W) != 0 : false;
-        if (mine) {
-            if (o0 >= 0) red_add(maps + o0 + q, a0);
-            if (o1 >= 0) red_add(maps + o1 + q, a1);
-            if (o2 >= 0) red_add(maps + o2 + q, a2);
-            if (o3 >= 0) red_add(maps + o3 + q, a3);
-        }
+        const int lanes = ((sums & PNM_SUM_WD) ? 1 : 0) | ((sums & PNM_SUM_WD2) ? 2 : 0) | ((sums & PNM_SUM_W) ? 4 : 0);
+        quad_reduce<A>(maps, off, s1, s2, has0 ? s0 : A(0), A(0), lane, lanes);
         off = -1;
     }
     // add one contribution; returns true when the pixel changed, i.e. the previous run (moved to `prev`) is due
@@ -297,6 +305,14 @@ struct MapRun {
     }
 };
 
+// one particle's record in the interleaved cube (PNM_CUBE_MOMENTS)
+template <int ACC>
+struct CubeRec {
+    using A = typename AccT<ACC>::type;
+    int off = -1;
+    A w0 = 0, w1 = 0, s1 = 0, s2 = 0;
+};
+
 // ---- per-thread binning context: everything loop invariant sits in registers -------------------
 // SUMS >= 0: the set of sums is a compile-time constant (hot configurations); -1: read at run time.
 template <typename T, int ACC, int SUMS>
@@ -315,10 +331,25 @@ struct Binner {
     }
     __device__ __forceinline__ int sums() const { return SUMS >= 0 ? SUMS : rsums; }
 
+    // w*d and w*(d*d), each product rounded in the particle dtype (grid.py:128, :131) -- or in float32 when the
+    // values are float32 carried as float64 (PNM_VAL_D32 / PNM_VAL_W32: numpy's result types)
+    __device__ __forceinline__ static void weighted_terms(int sm, T w, T d, T& wd, T& wdd) {
+        T dd = mul_rn(d, d);
+        if (sizeof(T) == 8 && (sm & PNM_VAL_D32)) {
+            dd = (T)__fmul_rn((float)d, (float)d);
+            if (sm & PNM_VAL_W32) {
+                wd = (T)__fmul_rn((float)w, (float)d);
+                wdd = (T)__fmul_rn((float)w, (float)dd);
+                return;
+            }
+        }
+        wd = mul_rn(w, d); wdd = mul_rn(w, dd);
+    }
+
     // (px, py, d) already projected: locate the bins, then reduce
     __device__ __forceinline__ void scatter(A* maps, A* cube, MapRun<ACC>& run, TmaStage<ACC>& st,
                                             T px, T py, T d, T w, bool masked_in,
-                                            MapRun<ACC>* prev = nullptr, bool* due = nullptr) {
+                                            MapRun<ACC>* prev = nullptr, bool* due = nullptr, CubeRec<ACC>* mom = nullptr) {
         if (masked_in) {
             if (mask_mode == PNM_MASK_PLAIN) return;
             if (mask_mode == PNM_MASK_AND_NONFINITE && !is_finite(d)) return;
@@ -336,16 +367,30 @@ struct Binner {
         }
         if ((unsigned)ix >= (unsigned)nx || (unsigned)iy >= (unsigned)ny) return;
         const bool in_v = want_v && (unsigned)iv < (unsigned)av.n;
+        if (sm & PNM_CUBE_MOMENTS) {
+            // interleaved cube: record (iv / 2, pixel) = { w of the even bin, w of the odd bin, sum w*d, sum w*d*d }.
+            // A particle inside the V range touches ONE sector; outside it, its three sums go to the (remainder) maps.
+            T wd, wdd;
+            weighted_terms(sm, w, d, wd, wdd);
+            const A aw = to_acc<ACC>(w, sc0), a1 = to_acc<ACC>(wd, sc1), a2 = to_acc<ACC>(wdd, sc2);
+            if (in_v) {
+                const int coff = ((iv >> 1) * npix + ix * ny + iy) * 4;
+                if (PNM_PAIRED && mom) {
+                    mom->off = coff; mom->w0 = (iv & 1) ? A(0) : aw; mom->w1 = (iv & 1) ? aw : A(0); mom->s1 = a1; mom->s2 = a2;
+                } else {
+                    red_add(cube + coff + (iv & 1), aw); red_add(cube + coff + 2, a1); red_add(cube + coff + 3, a2);
+                }
+            } else if (PNM_PAIRED && prev) {
+                prev->off = (iy * nx + ix) * PNM_MAP_SLOTS; prev->s0 = aw; prev->s1 = a1; prev->s2 = a2; prev->has0 = true;
+            } else {
+                run.add(maps, sm, st, (iy * nx + ix) * PNM_MAP_SLOTS, true, aw, a1, a2);
+            }
+            return;
+        }
         if (sm & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2)) {
             const bool use0 = (sm & PNM_SUM_W) && !((sm & PNM_W_FROM_CUBE) && in_v);
-            T dd = mul_rn(d, d), wd, wdd;
-            if (sizeof(T) == 8 && (sm & PNM_VAL_D32)) {         // numpy rounds `vm**2` in the dtype of v (grid.py:131)
-                dd = (T)__fmul_rn((float)d, (float)d);
-                if (sm & PNM_VAL_W32) {                         // ... and `wm * vm`, `wm * vm**2` in float32 when both are
-                    wd = (T)__fmul_rn((float)w, (float)d);
-                    wdd = (T)__fmul_rn((float)w, (float)dd);
-                } else { wd = mul_rn(w, d); wdd = mul_rn(w, dd); }
-            } else { wd = mul_rn(w, d); wdd = mul_rn(w, dd); }
+            T wd, wdd;
+            weighted_terms(sm, w, d, wd, wdd);
             const int off = (iy * nx + ix) * PNM_MAP_SLOTS;
             if (PNM_PAIRED && due)                              // paired mode: a finished run goes back to the caller
                 *due = run.add_deferred(*prev, off, use0, to_acc<ACC>(w, sc0), to_acc<ACC>(wd, sc1), to_acc<ACC>(wdd, sc2));
@@ -494,6 +539,25 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
                     parity ^= 1;
                 }
                 MapRun<ACC> run;
+                if (B.sums() & PNM_CUBE_MOMENTS) {
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) {
+                        CubeRec<ACC> rec;
+                        MapRun<ACC> rem;                   // a particle outside the V range: its sums go to the maps
+                        if (live) {
+                            T px = x[k], py = y[k], d = vx[k];
+                            if (FUSED) {
+                                px = rot_row(m[0], m[1], m[2], x[k], y[k], z[k]);
+                                py = rot_row(m[3], m[4], m[5], x[k], y[k], z[k]);
+                                d = rot_row(m[6], m[7], m[8], vx[k], vy[k], vz[k]);
+                            }
+                            bool due = false;
+                            B.scatter(maps0, cube0, run, st, px, py, d, W ? w[k] : (T)1, false, &rem, &due, &rec);
+                        }
+                        quad_reduce<A>(cube0, rec.off, rec.w0, rec.w1, rec.s1, rec.s2, lane, 15);
+                        if (__any_sync(0xffffffffu, rem.off >= 0)) rem.flush_quad(maps0, B.sums(), lane);
+                    }
+                } else
 #pragma unroll
                 for (int k = 0; k < VN; ++k) {
                     MapRun<ACC> prev;

@@ -188,15 +188,17 @@ int pnm_project_host(int device, int64_t n, int dtype,
     if (rc != PNM_OK) return rc;   // message already set by pnm_grid_create
 
     const int64_t maps_elems = pnm_maps_acc_elems(grid), cube_elems = pnm_cube_acc_elems(grid);
+    // maps + cube together: interleaved cube with the moments of the in-range particles (one L2 request each)
+    const int64_t cacc_elems = (want_maps && want_cube) ? pnm_cube_moments_acc_elems(grid) : cube_elems;
     const int64_t npix = (int64_t)nx * ny;
     // arena: [maps acc | cube acc | M V S | cube out | smoothing out | smoothing scratch]
-    const size_t arena_bytes = (size_t)(maps_elems + cube_elems + 3 * npix + cube_elems + (smooth ? 2 * cube_elems : 0)) * 8;
+    const size_t arena_bytes = (size_t)(maps_elems + cacc_elems + 3 * npix + cube_elems + (smooth ? 2 * cube_elems : 0)) * 8;
     rc = ensure_ring(device, (size_t)kChunk * 8, arena_bytes);
     if (rc != PNM_OK) { pnm_grid_destroy(grid); return rc; }
     char* arena = static_cast<char*>(g_ring.arena);
     void* acc_maps = arena;
     void* acc_cube = arena + (size_t)maps_elems * 8;
-    double* out_maps = reinterpret_cast<double*>(arena + (size_t)(maps_elems + cube_elems) * 8);
+    double* out_maps = reinterpret_cast<double*>(arena + (size_t)(maps_elems + cacc_elems) * 8);
     double* cube_out = out_maps + 3 * npix;
     double* smooth_out = cube_out + cube_elems;
     double* smooth_work = smooth_out + cube_elems;
@@ -204,10 +206,10 @@ int pnm_project_host(int device, int64_t n, int dtype,
     int sums = 0;
     if (want_maps) sums |= PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2;
     if (want_cube) sums |= PNM_SUM_CUBE;
-    if (want_maps && want_cube) sums |= PNM_W_FROM_CUBE;
+    if (want_maps && want_cube) sums |= PNM_W_FROM_CUBE | PNM_CUBE_MOMENTS;
 
     cudaStream_t s0 = g_ring.stream[0];
-    cudaError_t e = cudaMemsetAsync(arena, 0, (size_t)(maps_elems + cube_elems) * 8, s0);
+    cudaError_t e = cudaMemsetAsync(arena, 0, (size_t)(maps_elems + cacc_elems) * 8, s0);
     if (e == cudaSuccess)
         rc = accumulate_locked(grid, device, n, dtype, src, mats_host, nchain, sums, acc_mode, scales3_host,
                                want_maps ? acc_maps : nullptr, want_cube ? acc_cube : nullptr, s0);
@@ -219,7 +221,7 @@ int pnm_project_host(int device, int64_t n, int dtype,
             if (hosts[k]) e = cudaMemcpyAsync(hosts[k], out_maps + k * npix, (size_t)npix * 8, cudaMemcpyDeviceToHost, s0);
     }
     if (e == cudaSuccess && rc == PNM_OK && want_cube) {
-        rc = pnm_finalize_cube(grid, acc_cube, acc_mode, acc_mode == PNM_ACC_FIXED ? scales3_host[0] : 1.0, cube_out, s0);
+        rc = pnm_finalize_cube(grid, acc_cube, sums, acc_mode, acc_mode == PNM_ACC_FIXED ? scales3_host[0] : 1.0, cube_out, s0);
         const double* result = cube_out;
         if (rc == PNM_OK && smooth) {
             rc = pnm_smooth_cube(result, smooth_out, smooth_work, nx, ny, nv, taps0_host, ntaps0, taps1_host, ntaps1, s0);

@@ -52,19 +52,54 @@ __global__ void __launch_bounds__(256) k_finalize_vmaps(const void* acc_maps, co
                                                         double* M, double* V, double* S, double* S1o, double* S2o) {
     using A = typename AccT<ACC>::type;
     __shared__ A part[8][32];
+    __shared__ A part1[8][32];
+    __shared__ A part2[8][32];
     const int q = blockIdx.x * 32 + threadIdx.x;             // = ix*ny + iy
     const int npix = nx * ny;
-    A t = 0;
-    if (w_from_cube && q < npix) {
+    A t = 0, t1 = 0, t2 = 0;
+    if (w_from_cube == 2 && q < npix) {
+        // interleaved cube (PNM_CUBE_MOMENTS): records [g][q] = { w even, w odd, sum w*d, sum w*d*d }
+        const A* c = reinterpret_cast<const A*>(acc_cube);
+        for (int g = threadIdx.y; g < (nv + 1) / 2; g += 8) {
+            const A* rec = c + ((int64_t)g * npix + q) * 4;
+            t += rec[0] + rec[1]; t1 += rec[2]; t2 += rec[3];
+        }
+    } else if (w_from_cube && q < npix) {
         const A* c = reinterpret_cast<const A*>(acc_cube);
         for (int k = threadIdx.y; k < nv; k += 8) t += c[(int64_t)k * npix + q];
     }
     part[threadIdx.y][threadIdx.x] = t;
+    if (w_from_cube == 2) { part1[threadIdx.y][threadIdx.x] = t1; part2[threadIdx.y][threadIdx.x] = t2; }
     __syncthreads();
     if (threadIdx.y != 0 || q >= npix) return;
     const int ix = q / ny, iy = q - ix * ny;
     const int pix = iy * nx + ix;                            // map layout [iy][ix] (the reference's .T)
     double s0;
+    if (w_from_cube == 2) {
+        // all three sums = what the particles outside the V range left in the maps + the V-sums of the cube records
+        const A* m = reinterpret_cast<const A*>(acc_maps);
+        const int64_t stride = (int64_t)npix * PNM_MAP_SLOTS;
+        A tot0 = 0, tot1 = 0, tot2 = 0;
+        for (int r = 0; r < replicas; ++r) {
+            const A* rec = m + r * stride + (int64_t)pix * PNM_MAP_SLOTS;
+            tot0 += rec[kSlotS0]; tot1 += rec[kSlotS1]; tot2 += rec[kSlotS2];
+        }
+        for (int k = 0; k < 8; ++k) { tot0 += part[k][threadIdx.x]; tot1 += part1[k][threadIdx.x]; tot2 += part2[k][threadIdx.x]; }
+        const double s0m = (ACC == PNM_ACC_F64) ? (double)tot0 : __dmul_rn((double)tot0, is0);
+        const double s1m = (ACC == PNM_ACC_F64) ? (double)tot1 : __dmul_rn((double)tot1, is1);
+        const double s2m = (ACC == PNM_ACC_F64) ? (double)tot2 : __dmul_rn((double)tot2, is2);
+        double vm = 0.0, sm = 0.0;
+        if (s0m != 0.0) {
+            vm = __ddiv_rn(s1m, s0m);
+            sm = __dsqrt_rn(__dsub_rn(__ddiv_rn(s2m, s0m), __dmul_rn(vm, vm)));
+        }
+        if (M) M[pix] = s0m;
+        if (V) V[pix] = vm;
+        if (S) S[pix] = sm;
+        if (S1o) S1o[pix] = s1m;
+        if (S2o) S2o[pix] = s2m;
+        return;
+    }
     if (w_from_cube) {
         // sum w = remainder outside the V range (slot 0 of every replica) + the V-sum of the cube
         const A* m = reinterpret_cast<const A*>(acc_maps);
@@ -155,14 +190,16 @@ __global__ void __launch_bounds__(256) k_amr_repeat(const T* __restrict__ v, int
 // cube accumulator [iv][q] -> reference layout [q][iv] = cube[ix][iy][iv] (grid.py:259) as float64:
 // 32x32 shared-memory tile transpose, both sides coalesced.
 template <int ACC>
-__global__ void __launch_bounds__(256) k_cube_out(const void* acc_cube, double* out, int npix, int nv, double inv_scale) {
+__global__ void __launch_bounds__(256) k_cube_out(const void* acc_cube, double* out, int npix, int nv, double inv_scale,
+                                                  int moments) {
     __shared__ double tile[32][33];
     const int q0 = blockIdx.x * 32, v0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int iv = v0 + r, q = q0 + threadIdx.x;
         double val = 0.0;
         if (iv < nv && q < npix) {
-            const int64_t at = (int64_t)iv * npix + q;
+            // plain: [iv][q]; interleaved (PNM_CUBE_MOMENTS): slot iv & 1 of record [iv / 2][q]
+            const int64_t at = moments ? ((int64_t)(iv >> 1) * npix + q) * 4 + (iv & 1) : (int64_t)iv * npix + q;
             val = (ACC == PNM_ACC_F64) ? reinterpret_cast<const double*>(acc_cube)[at]
                                        : __dmul_rn((double)reinterpret_cast<const long long*>(acc_cube)[at], inv_scale);
         }

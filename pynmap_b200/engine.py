@@ -132,6 +132,11 @@ class Grid(object):
     def cube_elems(self):
         return self.nx * self.ny * self.nv
 
+    @property
+    def cube_moments_elems(self):
+        """Interleaved cube (CUBE_MOMENTS): records {w even bin, w odd bin, sum w*d, sum w*d*d} per (iv // 2, pixel)."""
+        return self.nx * self.ny * ((self.nv + 1) // 2) * 4
+
     def centres(self):
         """Pixel centres (grid.py:141-142, :247-249); fresh arrays, the caller may keep them."""
         px = np.linspace(self.limXY[0], self.limXY[1], self.nx)
@@ -224,9 +229,10 @@ def new_accumulators(grid, sums, acc, nviews=1):
     want_maps = bool(sums & (_lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2))
     want_cube = bool(sums & _lib.SUM_CUBE)
     if nviews == 1 and want_maps and want_cube:
-        pad = grid.cube_elems % 2        # keep the maps part 16-byte aligned (TMA bulk reductions)
-        flat = torch.zeros(grid.cube_elems + pad + grid.maps_elems, dtype=acc.dtype, device=grid.device)
-        return flat[grid.cube_elems + pad:], flat[:grid.cube_elems]
+        ncube = grid.cube_moments_elems if sums & _lib.CUBE_MOMENTS else grid.cube_elems
+        pad = ncube % 2                  # keep the maps part 16-byte aligned (TMA bulk reductions)
+        flat = torch.zeros(ncube + pad + grid.maps_elems, dtype=acc.dtype, device=grid.device)
+        return flat[ncube + pad:], flat[:ncube]
     maps = cube = None
     if want_maps:
         maps = torch.zeros(nviews * grid.maps_elems, dtype=acc.dtype, device=grid.device)
@@ -325,11 +331,12 @@ def finalize_map(grid, maps, acc, scales):
     return W, D, DW
 
 
-def finalize_cube(grid, cube, acc, scales):
-    """velocity-major accumulator -> float64 (nX, nY, nV) device tensor (np.histogramdd layout)."""
+def finalize_cube(grid, cube, acc, scales, sums=0):
+    """cube accumulator (velocity-major, or interleaved with the moments when ``sums`` has CUBE_MOMENTS) ->
+    float64 (nX, nY, nV) device tensor (np.histogramdd layout)."""
     out = torch.empty((grid.nx, grid.ny, grid.nv), dtype=torch.float64, device=grid.device)
     scale = float(scales[0]) if acc.code == _lib.ACC_FIXED else 1.0
-    _lib.call("pnm_finalize_cube", grid.handle, ptr(cube), acc.code, scale, ptr(out), stream_ptr())
+    _lib.call("pnm_finalize_cube", grid.handle, ptr(cube), int(sums), acc.code, scale, ptr(out), stream_ptr())
     return out
 
 

@@ -89,7 +89,7 @@ def project_host(arrays, PA, inclination, limXY, nXY, limV=None, nV=0, accumulat
         return res
 
     grid = engine.get_grid(limXY, nx, ny, limV, nv)
-    sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2 | ((_lib.SUM_CUBE | _lib.W_FROM_CUBE) if nv else 0)
+    sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2 | ((_lib.SUM_CUBE | _lib.W_FROM_CUBE | _lib.CUBE_MOMENTS) if nv else 0)
     maps, cube = engine.new_accumulators(grid, sums, acc)
     _lib.call("pnm_accumulate_host", grid.handle, device, n, code, *ptrs, matp, 1, sums, acc.code, sc,
               engine.ptr(maps), engine.ptr(cube), engine.stream_ptr())
@@ -100,7 +100,7 @@ def project_host(arrays, PA, inclination, limXY, nXY, limV=None, nV=0, accumulat
     for k, t in (("M", M), ("V", V), ("S", S)):
         _copy_out(res[k], t)
     if nv:
-        c = engine.finalize_cube(grid, cube, acc, scales)
+        c = engine.finalize_cube(grid, cube, acc, scales, sums)
         if taps0 is not None:
             c = engine.smooth_cube(c, taps0, taps1)
         _copy_out(res["cube"], c)

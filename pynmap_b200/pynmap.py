@@ -495,6 +495,11 @@ class snapshot(object):
         grid = engine.get_grid(limXY, n2[0], n2[1], limV, int(nV))
         w = self._weights_on_device(weights)
         sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2 | _lib.SUM_CUBE | _lib.W_FROM_CUBE
+        if not self._memory_ordered(grid, reducer):
+            # particles in no particular order: all three sums of a particle into ONE sector of the interleaved cube.
+            # Spatially ordered snapshots (tree / space-filling-curve order) keep the plain cube + replicated maps,
+            # where consecutive particles of a pixel merge in registers and hot pixels are spread over replicas.
+            sums |= _lib.CUBE_MOMENTS
         scales = None
         if acc.code == _lib.ACC_FIXED:
             # sharded fixed-point runs agree on the global particle count and bounds (cached: the
@@ -515,6 +520,25 @@ class snapshot(object):
         with torch.cuda.stream(post_stream):
             return self._project_post(grid, maps, cube, sums, acc, scales, reducer)
 
+    def _memory_ordered(self, grid, reducer=None):
+        """True when neighbours in memory are neighbours in space (median distance between consecutive particles
+        below one pixel), estimated once per snapshot and pixel size on a strided sample of 65536 pairs.  Sharded
+        runs agree on one answer (any rank ordered -> all use the plain layout): the partial grids are summed."""
+        pos = self._base[0]
+        pix = min((grid.limXY[1] - grid.limXY[0]) / max(grid.nx - 1, 1), (grid.limXY[3] - grid.limXY[2]) / max(grid.ny - 1, 1))
+        key = ("ordered", id(pos), float(pix), id(reducer))
+        if key not in self._absmax:
+            n = self.npart
+            ordered = False
+            if n >= 8192:
+                idx = torch.arange(0, n - 1, max(1, (n - 1) // 65536), device=pos[0].device)
+                d2 = sum((pos[k][idx + 1] - pos[k][idx]).double() ** 2 for k in range(3))
+                ordered = bool(torch.sqrt(d2).median().item() < pix)
+            if reducer is not None:
+                ordered = bool(reducer.reduce_max(float(ordered))[0] > 0.5)
+            self._absmax[key] = ordered
+        return self._absmax[key]
+
     def _project_post(self, grid, maps, cube, sums, acc, scales, reducer):
         """Everything after the scatter of project(): fold + reduce over ranks, finalisation."""
         if reducer is not None:
@@ -528,7 +552,7 @@ class snapshot(object):
         newmap = SnapMap(name="Velocity moments", input_dic={"X": X, "Y": Y, "V": V, "M": M, "S": S,
                                                               "PAs": self.PAs, "inclinations": self.inclinations})
         px, py, pv = grid.centres()
-        mylosvd = LOSVD(px, py, pv, self._out(engine.finalize_cube(grid, cube, acc, scales)))
+        mylosvd = LOSVD(px, py, pv, self._out(engine.finalize_cube(grid, cube, acc, scales, sums)))
         mylosvd.PAs, mylosvd.inclinations = self.PAs, self.inclinations
         return newmap, mylosvd
 

@@ -188,7 +188,7 @@ def test_non_uniform_edges_through_the_abi(env):
               _lib.doubles(scales), P(maps), P(cube), engine.stream_ptr())
     _lib.call("pnm_fold_maps", h, P(maps), _lib.ACC_FIXED, 1, engine.stream_ptr())
     out = torch.empty((40, 30, 5), dtype=torch.float64, device="cuda")
-    _lib.call("pnm_finalize_cube", h, P(cube), _lib.ACC_FIXED, float(scales[0]), P(out), engine.stream_ptr())
+    _lib.call("pnm_finalize_cube", h, P(cube), _lib.SUM_CUBE, _lib.ACC_FIXED, float(scales[0]), P(out), engine.stream_ptr())
     omaps, ocube = oc.project_bin(pts, w, None, 1, 1, ex, ey, ev, 15, oc.ACC_FIXED, scales, fused=False)
     got = maps[:40 * 30 * 4].cpu().numpy().reshape(30, 40, 4)
     assert R >= 1 and np.array_equal(got[..., [2, 0, 1]], omaps[0][..., :3])
@@ -218,7 +218,7 @@ def test_host_path_single_and_sharded_flavours(env):
         return True
     sharded = hostpath.project_host([pinned[k] for k in range(7)], 30., 60., wl.LIM_XY, 64, wl.LIM_V, 32,
                                     smooth_fwhm=(1.0, 1.0), reducer=fake_reducer)
-    assert calls == [[64 * 64 * 32 + 64 * 64 * 4]]       # one contiguous span: cube + folded maps
+    assert calls == [[64 * 64 * 16 * 4 + 64 * 64 * 4]]   # one contiguous span: interleaved cube (nV/2 records of 4) + folded maps
     for res in (single, sharded):
         assert close(res["M"], vm.M) and rel_err(res["V"], vm.V, floor=1e-3) < 1e-9
         assert np.allclose(res["cube"], sm.losvd, rtol=1e-10, atol=1e-12 * sm.losvd.max())
@@ -256,7 +256,7 @@ def test_sharded_project_with_post_stream_matches_plain(env):
     hook.reduce_max = lambda *v: v
     vm1, lv1 = whole.project(reducer=hook, post_stream=post, **kw)
     post.synchronize()
-    assert seen == [96 * 96 * 64 + 96 * 96 * 4]           # one contiguous span: cube + the folded map replica
+    assert seen == [96 * 96 * 32 * 4 + 96 * 96 * 4]       # one contiguous span: interleaved cube + the folded map replica
     for a, b in ((vm0.M, vm1.M), (vm0.V, vm1.V), (vm0.S, vm1.S), (lv0.losvd, lv1.losvd)):
         assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
 
@@ -268,7 +268,7 @@ def test_sharded_project_with_post_stream_matches_plain(env):
         parts["a"] = [t.clone() for t in tensors]
         return False
     hook_a.n_total = lambda n_local: n
-    hook_a.reduce_max = lambda *v: (max(v[0], bounds[0]), max(v[1], bounds[1]))
+    hook_a.reduce_max = lambda *v: (max(v[0], bounds[0]), max(v[1], bounds[1])) if len(v) == 2 else v   # scales | layout vote
 
     def hook_b(*tensors):
         for t, other in zip(tensors, parts["a"]):
@@ -284,4 +284,26 @@ def test_sharded_project_with_post_stream_matches_plain(env):
     hook.reduce_max = hook_a.reduce_max
     vm3, lv3 = whole2.project(reducer=hook, **kw)         # same global bounds -> same fixed-point scales
     for a, b in ((vm3.M, vm2.M), (vm3.V, vm2.V), (vm3.S, vm2.S), (lv3.losvd, lv2.losvd)):
+        assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+
+
+def test_ordered_snapshot_uses_plain_layout_same_results(env):
+    """A Morton-ordered copy of a snapshot takes the plain cube + replicated maps (run merging), the unordered one
+    the interleaved cube; in fixed point both give the same bits."""
+    import pynmap_b200 as pnm
+    import workloads
+    from pynmap_b200 import _lib, engine
+    n = 2_000_000
+    soa = workloads.make_snapshot(n, seed=17, device="cuda")
+    srt = workloads.morton_sort(soa)
+    kw = dict(weight_name="mass", limXY=workloads.LIM_XY, nXY=64, limV=workloads.LIM_V, nV=48, accumulate="fixed")
+    out = []
+    for data, want_ordered in ((soa, False), (srt, True)):
+        s = pnm.snapshot.from_arrays(data[:3], data[3:6], mass=data[6], output="torch")
+        s.rotate(PA=30., inclination=60.)
+        grid = engine.get_grid(workloads.LIM_XY, 64, 64, workloads.LIM_V, 48)
+        assert s._memory_ordered(grid) is want_ordered
+        out.append(s.project(**kw))
+    (vm_a, lv_a), (vm_b, lv_b) = out
+    for a, b in ((vm_a.M, vm_b.M), (vm_a.V, vm_b.V), (vm_a.S, vm_b.S), (lv_a.losvd, lv_b.losvd)):
         assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
