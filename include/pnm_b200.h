@@ -73,8 +73,8 @@ extern "C" {
 /* With PNM_W_FROM_CUBE: the cube accumulator uses the INTERLEAVED layout [ceil(nv/2)][ix][iy][4] =
  * { w of velocity bin 2g, w of bin 2g+1, sum w*d, sum w*d*d } (pnm_cube_moments_acc_elems elements), so that all
  * three sums of a particle inside the V range fall into one 32-byte sector -- one L2 request per particle.  The maps
- * accumulator then only receives the particles outside the V range; pnm_finalize_vmaps / pnm_finalize_cube take the
- * same flag.                                                                                        */
+ * accumulator then only receives the particles outside the V range and is a single replica (ny*nx*PNM_MAP_SLOTS
+ * elements, no pnm_fold_maps needed); pnm_finalize_vmaps / pnm_finalize_cube take the same flag.   */
 #define PNM_CUBE_MOMENTS 256
 /* Mixed input dtypes (pnm_bin_points with dtype = PNM_F64 only).  numpy evaluates `wm * vm` and
  * `wm * vm**2` (grid.py:128-131, :201) in the result type of the two operands, which is float32 when

@@ -296,7 +296,7 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     const double* eps = dtype == PNM_F32 ? g->eps32 : g->eps64;
     p.eps_x = eps[0]; p.eps_y = eps[1]; p.eps_v = eps[2];
     p.sums = sums; p.nchain = fused ? nchain : 1; p.nviews = fused ? nviews : 1;
-    p.replicas = g->replicas;
+    p.replicas = (sums & PNM_CUBE_MOMENTS) ? 1 : g->replicas;   // the maps only take the few particles outside the V range
     p.rep_shift = env_int("PNM_REP_SHIFT", 5);
     // hybrid scatter: 16-byte TMA bulk reductions need a 16-byte aligned maps accumulator
     p.tma_slots = (acc_maps && (reinterpret_cast<uintptr_t>(acc_maps) & 15) == 0 && (sums & PNM_SUM_WD) && (sums & PNM_SUM_WD2))
@@ -344,7 +344,7 @@ int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_
     const int npix = g->nx * g->ny;
     const int grid = (npix + 31) / 32;
     const dim3 block(32, 8);
-    const int replicas = (sums & PNM_MAPS_FOLDED) ? 1 : g->replicas;
+    const int replicas = (sums & (PNM_MAPS_FOLDED | PNM_CUBE_MOMENTS)) ? 1 : g->replicas;
     if (acc_mode == PNM_ACC_F64) {
         pnm::k_finalize_vmaps<PNM_ACC_F64><<<grid, block, 0, as_stream(stream)>>>(acc_maps, acc_cube, g->nx, g->ny, g->nv,
                                                                               replicas, wfc, 1.0, 1.0, 1.0, M, V, S, S1, S2);

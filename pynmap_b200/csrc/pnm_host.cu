@@ -187,10 +187,11 @@ int pnm_project_host(int device, int64_t n, int dtype,
     int rc = pnm_grid_create(nx, ex, ny, ey, want_cube ? nv : 0, want_cube ? ev : nullptr, &grid);
     if (rc != PNM_OK) return rc;   // message already set by pnm_grid_create
 
-    const int64_t maps_elems = pnm_maps_acc_elems(grid), cube_elems = pnm_cube_acc_elems(grid);
+    const int64_t npix = (int64_t)nx * ny;
+    const int64_t cube_elems = pnm_cube_acc_elems(grid);
+    const int64_t maps_elems = (want_maps && want_cube) ? (int64_t)npix * PNM_MAP_SLOTS : pnm_maps_acc_elems(grid);   // one replica with the interleaved cube
     // maps + cube together: interleaved cube with the moments of the in-range particles (one L2 request each)
     const int64_t cacc_elems = (want_maps && want_cube) ? pnm_cube_moments_acc_elems(grid) : cube_elems;
-    const int64_t npix = (int64_t)nx * ny;
     // arena: [maps acc | cube acc | M V S | cube out | smoothing out | smoothing scratch]
     const size_t arena_bytes = (size_t)(maps_elems + cacc_elems + 3 * npix + cube_elems + (smooth ? 2 * cube_elems : 0)) * 8;
     rc = ensure_ring(device, (size_t)kChunk * 8, arena_bytes);

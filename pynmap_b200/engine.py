@@ -229,9 +229,11 @@ def new_accumulators(grid, sums, acc, nviews=1):
     want_maps = bool(sums & (_lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2))
     want_cube = bool(sums & _lib.SUM_CUBE)
     if nviews == 1 and want_maps and want_cube:
-        ncube = grid.cube_moments_elems if sums & _lib.CUBE_MOMENTS else grid.cube_elems
+        moments = bool(sums & _lib.CUBE_MOMENTS)
+        ncube = grid.cube_moments_elems if moments else grid.cube_elems
+        nmaps = grid.maps_fold_elems if moments else grid.maps_elems     # one replica: the maps only take the out-of-V rest
         pad = ncube % 2                  # keep the maps part 16-byte aligned (TMA bulk reductions)
-        flat = torch.zeros(ncube + pad + grid.maps_elems, dtype=acc.dtype, device=grid.device)
+        flat = torch.zeros(ncube + pad + nmaps, dtype=acc.dtype, device=grid.device)
         return flat[ncube + pad:], flat[:ncube]
     maps = cube = None
     if want_maps:

@@ -93,7 +93,8 @@ def project_host(arrays, PA, inclination, limXY, nXY, limV=None, nV=0, accumulat
     maps, cube = engine.new_accumulators(grid, sums, acc)
     _lib.call("pnm_accumulate_host", grid.handle, device, n, code, *ptrs, matp, 1, sums, acc.code, sc,
               engine.ptr(maps), engine.ptr(cube), engine.stream_ptr())
-    engine.fold_maps(grid, maps, acc, clear=False)
+    if not sums & _lib.CUBE_MOMENTS:
+        engine.fold_maps(grid, maps, acc, clear=False)
     if not reducer(*engine.reduce_span(grid, maps, cube)):
         return None
     M, V, S = engine.finalize_vmaps(grid, maps, cube, sums | _lib.MAPS_FOLDED, acc, scales)

@@ -542,7 +542,8 @@ class snapshot(object):
     def _project_post(self, grid, maps, cube, sums, acc, scales, reducer):
         """Everything after the scatter of project(): fold + reduce over ranks, finalisation."""
         if reducer is not None:
-            engine.fold_maps(grid, maps, acc, clear=False)     # single-use accumulators: nothing adds to them again
+            if not sums & _lib.CUBE_MOMENTS:                   # (the interleaved layout has a single map replica)
+                engine.fold_maps(grid, maps, acc, clear=False) # single-use accumulators: nothing adds to them again
             keep = reducer(*engine.reduce_span(grid, maps, cube))
             if not keep:
                 return None, None
