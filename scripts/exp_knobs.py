@@ -23,11 +23,12 @@ lib = os.path.basename(os.environ.get("PNM_B200_LIB", "default"))
 out = []
 for name, data, nxy, nv, sums, limV in (("none", soa, 128, 256, 8, [1e6, 1e6 + 1]), ("cube", soa, 128, 256, 8, workloads.LIM_V),
                                         ("maps3", soa, 128, 0, 7, workloads.LIM_V), ("full31", soa, 128, 256, 31, workloads.LIM_V),
-                                        ("maps3_256", soa, 256, 0, 7, workloads.LIM_V), ("sorted31", srt, 128, 256, 31, workloads.LIM_V)):
+                                        ("maps3_256", soa, 256, 0, 7, workloads.LIM_V), ("sorted31", srt, 128, 256, 31, workloads.LIM_V),
+                                        ("moments287", soa, 128, 256, 287, workloads.LIM_V), ("moments287_256x512", soa, 256, 512, 287, workloads.LIM_V)):
     if data is None: continue
     grid = engine.get_grid(workloads.LIM_XY, nxy, nxy, limV, nv)
     maps, cube = engine.new_accumulators(grid, sums | 1, f64)
-    if sums & 8: _, cube = engine.new_accumulators(grid, 8, f64)
+    if sums & 8 and not sums & 256: _, cube = engine.new_accumulators(grid, 8, f64)
     rows = [data[k] for k in range(6)]
     t = timeit(lambda: engine.project_bin(grid, rows, data[6], mat, 1, 1, sums, f64, None, maps, cube))
     out.append("%s=%.3f" % (name, t))
