@@ -307,3 +307,29 @@ def test_ordered_snapshot_uses_plain_layout_same_results(env):
     (vm_a, lv_a), (vm_b, lv_b) = out
     for a, b in ((vm_a.M, vm_b.M), (vm_a.V, vm_b.V), (vm_a.S, vm_b.S), (lv_a.losvd, lv_b.losvd)):
         assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+
+
+def test_interleaved_cube_odd_and_tiny_velocity_axes(env):
+    """snapshot.project on an unordered snapshot takes the interleaved cube (records of two velocity bins):
+    odd nV, nV = 2 and a V range that leaves most particles outside it, against the C oracle (fixed point: bit-exact)."""
+    import pynmap_b200 as pnm
+    import workloads
+    from pynmap_b200 import engine
+    n = 400_003
+    soa = workloads.make_snapshot(n, seed=23, device="cuda", unit_mass=False)
+    host = soa.cpu().numpy()
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="numpy")
+    snap.rotate(PA=30., inclination=60.)
+    mat = on.rotation_matrix(np.float32(30.), np.float32(60.))
+    lim = workloads.LIM_XY
+    for nv, limv in ((21, [-500., 500.]), (2, [-50., 50.]), (7, [100., 160.])):
+        grid = engine.get_grid(lim, 40, 24, limv, nv)
+        assert not snap._memory_ordered(grid)
+        vm, lv = snap.project(weight_name="mass", limXY=lim, nXY=[40, 24], limV=limv, nV=nv, accumulate="fixed")
+        scales = snap._fixed_scales(engine.AccMode("fixed"), snap.mass)
+        ex, ey, ev = on.bin_edges(lim[0], lim[1], 40), on.bin_edges(lim[2], lim[3], 24), on.bin_edges(limv[0], limv[1], nv)
+        omaps, ocube = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, ex, ey, ev, 15 | 16, oc.ACC_FIXED, scales)
+        Mo, Vo, So = oc.finalize_vmaps(omaps[0], ocube[0], 15 | 16, oc.ACC_FIXED, scales)
+        assert np.array_equal(vm.M, Mo) and np.array_equal(vm.V, Vo) and np.array_equal(vm.S, So, equal_nan=True)
+        assert np.array_equal(lv.losvd, ocube[0].astype(np.float64) * (1.0 / scales[0]))
+        assert lv.losvd.shape == (40, 24, nv) and 0 < lv.losvd.sum() <= vm.M.sum() * (1 + 1e-12)
