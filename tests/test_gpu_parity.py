@@ -480,3 +480,35 @@ def test_mixed_dtypes_follow_numpy_result_types(pnm):
     _, _, _, V64, _ = on.points_2vmaps(x, y, v32.astype(np.float64), weights=w32.astype(np.float64), limXY=lim, nXY=20)
     _, _, _, V32, _ = on.points_2vmaps(x, y, v32, weights=w32, limXY=lim, nXY=20)
     assert np.nanmax(np.abs(V64 - V32)) > 1e-8
+
+
+def test_tma_bulk_reduction_path_still_exact(pnm, monkeypatch):
+    """The TMA bulk-reduction hand-off (off by default since lane pairs / quads made it redundant) stays selectable
+    with PNM_TMA_SLOTS and exact: it serves the lane-pair mode (maps + plain cube, 16-byte records); maps-only runs use
+    lane quads and ignore it."""
+    import workloads
+    from pynmap_b200 import _lib, engine
+    n = 1_000_003
+    soa = workloads.make_snapshot(n, seed=29, device="cuda", unit_mass=False)
+    host = soa.cpu().numpy()
+    mat = on.rotation_matrix(np.float32(30.0), np.float32(60.0))
+    grid = engine.get_grid(workloads.LIM_XY, 48, 40, workloads.LIM_V, 24)
+    fx = engine.AccMode("fixed")
+    scales = engine.fixed_scales(n, engine.absmax(soa[6]), 2.0 * max(engine.absmax(soa[k]) for k in (3, 4, 5)))
+    rows = [soa[k] for k in range(6)]
+    ref = {}
+    for slots in ("0", "2", "4"):
+        monkeypatch.setenv("PNM_TMA_SLOTS", slots)
+        for sums in (7, 31):
+            maps, cube = engine.new_accumulators(grid, sums, fx)
+            engine.project_bin(grid, rows, soa[6], mat, 1, 1, sums, fx, scales, maps, cube)
+            out = engine.finalize_vmaps(grid, maps, cube if sums & 8 else None, sums, fx, scales)
+            got = [t.cpu().numpy() for t in out] + ([engine.finalize_cube(grid, cube, fx, scales, sums).cpu().numpy()] if sums & 8 else [])
+            if slots == "0":
+                ref[sums] = got
+            else:
+                assert all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, ref[sums])), (slots, sums)
+    omaps, ocube = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, grid.edges_x, grid.edges_y, grid.edges_v, 31,
+                                  oc.ACC_FIXED, scales)
+    Mo, Vo, So = oc.finalize_vmaps(omaps[0], ocube[0], 31, oc.ACC_FIXED, scales)
+    assert np.array_equal(ref[31][0], Mo) and np.array_equal(ref[31][1], Vo) and np.array_equal(ref[31][2], So, equal_nan=True)
