@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): a seeded synthetic disk+
 10^8 float32 particles PER GPU (weak scaling), rotate(PA=30, incl=60) -> 128x128 mass / V / sigma
 maps + 128x128x256 LOSVD cube from ONE read of the particles -> Gaussian smoothing of the cube
 (convolve_spatial to FWHM 1 kpc).  At N > 1 every rank bins its own shard and the partial grids are
-summed with an NCCL reduce to rank 0, which finalises and smooths.
+summed with an NCCL reduce to the step's owner rank (step k -> rank k mod N), which finalises and smooths.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            our arm (default N=1, K=30, W=5)
   python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's CPU path (numpy)
@@ -385,10 +385,11 @@ def run_b200(args):
                                                    "peak_per_s": 1.87e11, "frac": 1.0 * n_local / (kernel_ms * 1e-3) / 1.87e11}},
             "cpu_baseline": base,
             "e2e": e2e,
-            # our kernels launched by rank 0 inside the timed region: k_project_bin (+ k_fold_maps when
-            # sharded) every step; k_finalize_vmaps, k_cube_out, k_smooth_axis<0>, <1> on the steps it owns
+            # our kernels launched by rank 0 inside the timed region: k_project_bin every step (no replica fold: the
+            # interleaved cube has a single map replica); k_finalize_vmaps, k_cube_out, k_smooth_axis<0>, <1> on the
+            # steps it owns
             "gpu_launches": (5 * args.steps if n_gpus == 1 else
-                             2 * args.steps + 4 * len([k for k in range(args.steps) if (k + max(3, args.warmup)) % n_gpus == 0])),
+                             args.steps + 4 * len([k for k in range(args.steps) if (k + max(3, args.warmup)) % n_gpus == 0])),
             "clocks": clocks,
             "extras": extras,
         }
