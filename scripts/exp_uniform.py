@@ -1,5 +1,5 @@
-"""Development experiment: the bench kernel (maps + cube, sums = 31) on a UNIFORM box of particles (no hot
-pixels) for several TMA shares -- separates address contention from unit throughput."""
+"""Development experiment: the scatter kernel on a UNIFORM box of particles (no hot pixels) and on the disk+bulge
+snapshot, per accumulator layout -- separates address contention from unit throughput."""
 import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,9 +27,11 @@ grid = engine.get_grid(workloads.LIM_XY, 128, 128, workloads.LIM_V, 256)
 out = []
 for name, data in (("uniform", soa), ("disk+bulge", disk)):
     rows = [data[k] for k in range(6)]
-    for slots in (0, 3, 4, 5, 6):
-        os.environ["PNM_TMA_SLOTS"] = str(slots)
-        maps, cube = engine.new_accumulators(grid, 31, f64)
-        t = timeit(lambda: engine.project_bin(grid, rows, data[6], mat, 1, 1, 31, f64, None, maps, cube))
-        out.append("%s slots=%d: %.3f ms" % (name, slots, t))
+    for label, sums in (("lane pairs, plain cube", 31), ("lane quads, interleaved cube", 31 | 256), ("maps only, lane quads", 7),
+                        ("cube only", 8)):
+        maps, cube = engine.new_accumulators(grid, sums | 1, f64)
+        if sums == 8:
+            _, cube = engine.new_accumulators(grid, 8, f64)
+        t = timeit(lambda: engine.project_bin(grid, rows, data[6], mat, 1, 1, sums, f64, None, maps, cube))
+        out.append("%-12s %-30s %.3f ms" % (name, label, t))
 print("\n".join(out))
