@@ -139,8 +139,8 @@ int pnm_fold_maps(const pnm_grid* g, void* acc_maps, int acc_mode, int clear_oth
  * For each of `nviews` views: apply `nchain` float32 matrices in sequence to (x,y,z) and
  * (vx,vy,vz) (each step rounded like pnm_rotate), take x' = pos'[0], y' = pos'[1],
  * d = vel'[2], then accumulate the sums selected by `sums` with weights w (NULL = 1):
- *   acc_maps [view][pnm_maps_acc_elems]   (double or int64 by acc_mode)
- *   acc_cube [view][pnm_cube_acc_elems]
+ *   acc_maps [view][pnm_maps_acc_elems]   (double or int64 by acc_mode; [view][ny*nx*PNM_MAP_SLOTS] with PNM_CUBE_MOMENTS)
+ *   acc_cube [view][pnm_cube_acc_elems]   ([view][pnm_cube_moments_acc_elems] with PNM_CUBE_MOMENTS)
  * mats_host: float32 [nviews][nchain][9] on the HOST.  scales3_host (FIXED only): the three
  * power-of-two scales for w, w*d, w*d*d.  Accumulators must be zeroed by the caller (or hold
  * earlier partial sums: calls add).  mask: optional uint8 per particle.                       */

@@ -307,7 +307,9 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     //  path is off unless PNM_TMA_SLOTS asks for it)
     for (int k = 0; k < 3; ++k) p.scale[k] = (acc_mode == PNM_ACC_FIXED) ? scales3_host[k] : 1.0;
     p.acc_maps = acc_maps; p.acc_cube = acc_cube;
-    p.maps_stride = pnm_maps_acc_elems(g); p.cube_stride = pnm_cube_acc_elems(g);
+    // per-view strides; with the interleaved cube the maps are a single replica and the cube holds 4-slot records
+    p.maps_stride = (sums & PNM_CUBE_MOMENTS) ? (int64_t)g->nx * g->ny * PNM_MAP_SLOTS : pnm_maps_acc_elems(g);
+    p.cube_stride = (sums & PNM_CUBE_MOMENTS) ? pnm_cube_moments_acc_elems(g) : pnm_cube_acc_elems(g);
     if (fused) memcpy(p.mats, mats_host, sizeof(float) * 9 * nchain * nviews);
 
     cudaStream_t st = as_stream(stream);

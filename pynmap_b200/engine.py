@@ -235,11 +235,12 @@ def new_accumulators(grid, sums, acc, nviews=1):
         pad = ncube % 2                  # keep the maps part 16-byte aligned (TMA bulk reductions)
         flat = torch.zeros(ncube + pad + nmaps, dtype=acc.dtype, device=grid.device)
         return flat[ncube + pad:], flat[:ncube]
+    moments = bool(sums & _lib.CUBE_MOMENTS)
     maps = cube = None
     if want_maps:
-        maps = torch.zeros(nviews * grid.maps_elems, dtype=acc.dtype, device=grid.device)
+        maps = torch.zeros(nviews * (grid.maps_fold_elems if moments else grid.maps_elems), dtype=acc.dtype, device=grid.device)
     if want_cube:
-        cube = torch.zeros(nviews * grid.cube_elems, dtype=acc.dtype, device=grid.device)
+        cube = torch.zeros(nviews * (grid.cube_moments_elems if moments else grid.cube_elems), dtype=acc.dtype, device=grid.device)
     return maps, cube
 
 

@@ -333,3 +333,28 @@ def test_interleaved_cube_odd_and_tiny_velocity_axes(env):
         assert np.array_equal(vm.M, Mo) and np.array_equal(vm.V, Vo) and np.array_equal(vm.S, So, equal_nan=True)
         assert np.array_equal(lv.losvd, ocube[0].astype(np.float64) * (1.0 / scales[0]))
         assert lv.losvd.shape == (40, 24, nv) and 0 < lv.losvd.sum() <= vm.M.sum() * (1 + 1e-12)
+
+
+def test_interleaved_cube_two_views_in_one_launch(env):
+    """pnm_project_bin with nviews = 2 and PNM_CUBE_MOMENTS (general kernel path, per-view strides of the interleaved
+    layout) == two single-view launches, bit for bit in fixed point."""
+    import workloads
+    from pynmap_b200 import _lib, engine
+    n = 300_000
+    soa = workloads.make_snapshot(n, seed=41, device="cuda", unit_mass=False)
+    rows = [soa[k] for k in range(6)]
+    grid = engine.get_grid(workloads.LIM_XY, 32, 48, workloads.LIM_V, 19)
+    fx = engine.AccMode("fixed")
+    scales = engine.fixed_scales(n, engine.absmax(soa[6]), 2.0 * max(engine.absmax(soa[k]) for k in (3, 4, 5)))
+    sums = 31 | _lib.CUBE_MOMENTS
+    mats = [on.rotation_matrix(np.float32(30.0), np.float32(60.0)), on.rotation_matrix(np.float32(75.0), np.float32(20.0))]
+    maps2, cube2 = engine.new_accumulators(grid, sums, fx, nviews=2)
+    engine.project_bin(grid, rows, soa[6], np.stack(mats), 1, 2, sums, fx, scales, maps2, cube2)
+    for k, mat in enumerate(mats):
+        maps1, cube1 = engine.new_accumulators(grid, sums, fx)
+        engine.project_bin(grid, rows, soa[6], mat, 1, 1, sums, fx, scales, maps1, cube1)
+        nm, nc = grid.maps_fold_elems, grid.cube_moments_elems
+        assert torch.equal(maps2[k * nm:(k + 1) * nm], maps1) and torch.equal(cube2[k * nc:(k + 1) * nc], cube1)
+        got = engine.finalize_vmaps(grid, maps2[k * nm:(k + 1) * nm], cube2[k * nc:(k + 1) * nc], sums, fx, scales)
+        want = engine.finalize_vmaps(grid, maps1, cube1, sums, fx, scales)
+        assert all(torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)) for a, b in zip(got, want))
