@@ -150,6 +150,7 @@ class snapshot(object):
             self.ML = self.compute_ml()
         self.mask = (self.mass == 0)
         self._absmax = {}
+        self._acc_pool = {}
         self.reset()
 
     @staticmethod
@@ -327,12 +328,13 @@ class snapshot(object):
             max_w, max_v = reduce_max(max_w, max_v)
         return engine.fixed_scales(n_total or self.npart, max_w, max_v)
 
-    def _run_fused(self, grid, w, sums, acc, scales, mats=None, nchain=None, nviews=1, mask=None, mask_mode=0):
+    def _run_fused(self, grid, w, sums, acc, scales, mats=None, nchain=None, nviews=1, mask=None, mask_mode=0,
+                   recycled=None):
         pos, vel = self._base
         if mats is None:
             mats = self._chain if self._chain else [np.eye(3, dtype=np.float32)]
             nchain = len(mats)
-        maps, cube = engine.new_accumulators(grid, sums, acc, nviews)
+        maps, cube = recycled if recycled is not None else engine.new_accumulators(grid, sums, acc, nviews)
         soa = (pos[0], pos[1], pos[2], vel[0], vel[1], vel[2])
         engine.project_bin(grid, soa, w, np.stack(mats), nchain, nviews, sums, acc, scales, maps, cube, mask, mask_mode)
         return maps, cube
@@ -509,16 +511,31 @@ class snapshot(object):
                 n_total, reduce_max = (reducer.n_total(self.npart), reducer.reduce_max) if reducer else (None, None)
                 self._absmax[key] = self._fixed_scales(acc, w, n_total, reduce_max)
             scales = self._absmax[key]
-        maps, cube = self._run_fused(grid, w, sums, acc, scales)
         if post_stream is None:
+            maps, cube = self._run_fused(grid, w, sums, acc, scales)
             return self._project_post(grid, maps, cube, sums, acc, scales, reducer)
+        # pipelined: the accumulators are recycled -- cleared on the post-processing stream once their results are
+        # out, so that no memset sits between two scatter kernels on the caller's stream
+        pool = self._acc_pool.setdefault((id(grid), sums, acc.code), [])
+        recycled = None
+        if len(pool) >= 2:                                   # the older of two sets: its clearing finished a step ago
+            maps, cube, cleared = pool.pop(0)
+            torch.cuda.current_stream().wait_event(cleared)
+            recycled = (maps, cube)
+        maps, cube = self._run_fused(grid, w, sums, acc, scales, recycled=recycled)
         scattered = torch.cuda.Event()
         scattered.record()                                   # on the caller's (scatter) stream
         post_stream.wait_event(scattered)
         for t in (maps, cube):                               # same storage; keep it alive for the other stream
             t.record_stream(post_stream)
         with torch.cuda.stream(post_stream):
-            return self._project_post(grid, maps, cube, sums, acc, scales, reducer)
+            out = self._project_post(grid, maps, cube, sums, acc, scales, reducer)
+            cube.zero_()
+            maps.zero_()
+            cleared = torch.cuda.Event()
+            cleared.record()
+        pool.append((maps, cube, cleared))
+        return out
 
     def _memory_ordered(self, grid, reducer=None):
         """True when neighbours in memory are neighbours in space (median distance between consecutive particles

@@ -358,3 +358,25 @@ def test_interleaved_cube_two_views_in_one_launch(env):
         got = engine.finalize_vmaps(grid, maps2[k * nm:(k + 1) * nm], cube2[k * nc:(k + 1) * nc], sums, fx, scales)
         want = engine.finalize_vmaps(grid, maps1, cube1, sums, fx, scales)
         assert all(torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)) for a, b in zip(got, want))
+
+
+def test_pipelined_project_recycles_accumulators_correctly(env):
+    """Several back-to-back project(post_stream=...) calls (accumulators recycled and cleared on the post-processing
+    stream) each return the same bits as a plain call, for both accumulator layouts."""
+    import pynmap_b200 as pnm
+    import workloads
+    n = 1_500_000
+    soa = workloads.make_snapshot(n, seed=57, device="cuda")
+    kw = dict(weight_name="mass", limXY=workloads.LIM_XY, nXY=64, limV=workloads.LIM_V, nV=40, accumulate="fixed")
+    post = torch.cuda.Stream(priority=-1)
+    for data in (soa, workloads.morton_sort(soa)):
+        snap = pnm.snapshot.from_arrays(data[:3], data[3:6], mass=data[6], output="torch")
+        snap.rotate(PA=30., inclination=60.)
+        vm0, lv0 = snap.project(**kw)
+        outs = [snap.project(post_stream=post, **kw) for _ in range(6)]
+        post.synchronize()
+        torch.cuda.synchronize()
+        for vm, lv in outs:
+            for a, b in ((vm0.M, vm.M), (vm0.V, vm.V), (vm0.S, vm.S), (lv0.losvd, lv.losvd)):
+                assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+        assert len(next(iter(snap._acc_pool.values()))) == 2          # two sets in rotation
