@@ -5,7 +5,7 @@ parity test reads:  gpu = pnm_project_bin(...); cpu = oracle_c.project_bin(...);
 Never imported by the product package.
 """
 import ctypes
-from ctypes import POINTER, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import c_int, c_int64, c_void_p
 
 import numpy as np
 

@@ -13,7 +13,6 @@ Additions: ``snapshot.from_arrays`` (tensors instead of an ascii file), the ``ac
 keyword ('f64' | 'fixed'), ``project`` (maps + LOSVD cube from a single read) and
 ``project_views`` (many viewing angles from a single read).
 """
-import copy
 import os
 from os.path import join as joinpath
 

@@ -12,7 +12,6 @@ every triangle's Clough-Tocher macro-element, restated from scipy's ``_clough_to
 everything per PARTICLE runs in the ``pnm_ct_interp`` kernel: point location through a uniform
 cell -> triangle index, barycentric coordinates, the cubic, and the nearest-node fill.
 """
-import ctypes
 import os
 
 import numpy as np
