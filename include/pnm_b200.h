@@ -3,7 +3,7 @@
  *
  * The reference (emsellem/pynmap) has no FFI layer: the path is four Python functions whose
  * arithmetic lives in numpy / astropy library calls.  Each entry point below replaces the BODY
- * of one of those calls; the Python host layer (pynmap_b200/*.py) keeps the reference's
+ * of one of those calls; the Python host layer (the pynmap_b200 package) keeps the reference's
  * signatures and binds these symbols with ctypes.  Citations are file:line in emsellem/pynmap.
  *
  *   pnm_rotate            np.dot(mat, pos.T).T                 pynmap/rotation.py:115-117, :67-69

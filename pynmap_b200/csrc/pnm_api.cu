@@ -49,13 +49,11 @@ inline int grid_for(int64_t work_items, int threads, int ctas_per_sm) {
 }
 
 // smallest T >= e (lower edges) / the exclusive upper bound equivalent to "<= e" (last edge)
-template <typename T> T thr_lower(double e);
-template <> float thr_lower<float>(double e) {
+float thr_lower_f32(double e) {
     float f = (float)e;
     if ((double)f < e) f = nextafterf(f, INFINITY);
     return f;
 }
-template <> double thr_lower<double>(double e) { return e; }
 // Guard band of the uniform bin guess g = (x - e0) * n / (en - e0), in units of bins: if the
 // fractional part of the COMPUTED g is further than this from 0 and 1, floor(g) is the true bin.
 // Two contributions: (1) how far the given edges deviate from the affine grid (np.linspace edges
@@ -157,7 +155,7 @@ int pnm_grid_create(int32_t nx, const double* ex, int32_t ny, const double* ey,
     int o = 0;
     for (int a = 0; a < 3; ++a) {
         if (ns[a] == 0) { t32[o] = 0.f; t64[o] = 0.0; o += 1; continue; }
-        for (int i = 0; i < ns[a]; ++i) { t32[o + i] = thr_lower<float>(es[a][i]); t64[o + i] = es[a][i]; }
+        for (int i = 0; i < ns[a]; ++i) { t32[o + i] = thr_lower_f32(es[a][i]); t64[o + i] = es[a][i]; }
         t32[o + ns[a]] = thr_last<float>(es[a][ns[a]]);
         t64[o + ns[a]] = thr_last<double>(es[a][ns[a]]);
         o += ns[a] + 1;
