@@ -201,7 +201,8 @@ struct TmaStage {
 // transpose the 4 x 4 values, so that lane q of the quad holds value #q of all four records, and four REDs follow,
 // each carrying one record in the quad's four lanes: L2 sees one request per record (red_pair_bench: one request
 // per distinct sector of an instruction).  off < 0: no record.  `lanes`: bit q set = value #q is wanted.
-template <typename A>
+// SLOT0_IN_OFF: value #0 goes to slot (off & 3) instead of slot 0 (the record itself starts at off & ~3).
+template <typename A, bool SLOT0_IN_OFF = false>
 __device__ __forceinline__ void quad_reduce(A* base, int off, A a0, A a1, A a2, A a3, int lane, int lanes) {
     const int q = lane & 3;
     {   // stage 1: partner lane ^ 1 -- even lanes keep (0, 2) and receive (1, 3), odd lanes the other way round
@@ -220,10 +221,18 @@ __device__ __forceinline__ void quad_reduce(A* base, int off, A a0, A a1, A a2, 
     const int o0 = __shfl_sync(0xffffffffu, off, qb), o1 = __shfl_sync(0xffffffffu, off, qb + 1);
     const int o2 = __shfl_sync(0xffffffffu, off, qb + 2), o3 = __shfl_sync(0xffffffffu, off, qb + 3);
     if ((lanes >> q) & 1) {
-        if (o0 >= 0) red_add(base + o0 + q, a0);
-        if (o1 >= 0) red_add(base + o1 + q, a1);
-        if (o2 >= 0) red_add(base + o2 + q, a2);
-        if (o3 >= 0) red_add(base + o3 + q, a3);
+        if (SLOT0_IN_OFF) {
+            const int keep = q == 0 ? ~0 : ~3;          // lane 0: the slot in the low bits; lanes 2, 3: slots 2, 3
+            if (o0 >= 0) red_add(base + (o0 & keep) + q, a0);
+            if (o1 >= 0) red_add(base + (o1 & keep) + q, a1);
+            if (o2 >= 0) red_add(base + (o2 & keep) + q, a2);
+            if (o3 >= 0) red_add(base + (o3 & keep) + q, a3);
+        } else {
+            if (o0 >= 0) red_add(base + o0 + q, a0);
+            if (o1 >= 0) red_add(base + o1 + q, a1);
+            if (o2 >= 0) red_add(base + o2 + q, a2);
+            if (o3 >= 0) red_add(base + o3 + q, a3);
+        }
     }
 }
 
@@ -309,8 +318,8 @@ struct MapRun {
 template <int ACC>
 struct CubeRec {
     using A = typename AccT<ACC>::type;
-    int off = -1;
-    A w0 = 0, w1 = 0, s1 = 0, s2 = 0;
+    int off = -1;          // record offset | (iv & 1): which of the record's two velocity bins takes w
+    A w = 0, s1 = 0, s2 = 0;
 };
 
 // ---- per-thread binning context: everything loop invariant sits in registers -------------------
@@ -376,7 +385,7 @@ struct Binner {
             if (in_v) {
                 const int coff = ((iv >> 1) * npix + ix * ny + iy) * 4;
                 if (PNM_PAIRED && mom) {
-                    mom->off = coff; mom->w0 = (iv & 1) ? A(0) : aw; mom->w1 = (iv & 1) ? aw : A(0); mom->s1 = a1; mom->s2 = a2;
+                    mom->off = coff | (iv & 1); mom->w = aw; mom->s1 = a1; mom->s2 = a2;
                 } else {
                     red_add(cube + coff + (iv & 1), aw); red_add(cube + coff + 2, a1); red_add(cube + coff + 3, a2);
                 }
@@ -554,7 +563,8 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
                             bool due = false;
                             B.scatter(maps0, cube0, run, st, px, py, d, W ? w[k] : (T)1, false, &rem, &due, &rec);
                         }
-                        quad_reduce<A>(cube0, rec.off, rec.w0, rec.w1, rec.s1, rec.s2, lane, 15);
+                        // three lanes per particle: lane 0 sends w to its velocity bin, lanes 2 and 3 the two moments
+                        quad_reduce<A, true>(cube0, rec.off, rec.w, A(0), rec.s1, rec.s2, lane, 13);
                         if (__any_sync(0xffffffffu, rem.off >= 0)) rem.flush_quad(maps0, B.sums(), lane);
                     }
                 } else
