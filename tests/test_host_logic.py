@@ -85,3 +85,28 @@ def test_bench_reference_arm_contract():
     other = subprocess.run(cmd, env=dict(env, RANK="1", WORLD_SIZE="2"), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                            text=True, timeout=600)
     assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def test_fitgh_parinfo_defaults_and_overrides():
+    """fit_losvd._parinfo: the start / limits / fixed arrays of fit_losvd.py:157-176 (NaN start = 'from the moments')."""
+    from pynmap_b200 import fit_losvd
+    x = np.linspace(-490.0, 490.0, 50)
+    info = fit_losvd._parinfo(x, 4)
+    assert np.isnan(info["start"][:2]).all() and list(info["start"][2:]) == [0.02, 0.02]
+    assert list(info["lo"]) == [-490.0, (x[1] - x[0]) / 3.0, -0.2, -0.2] or np.allclose(info["lo"], [-490.0, 20.0 / 3.0, -0.2, -0.2])
+    assert np.allclose(info["hi"], [490.0, 980.0 / 3.0, 0.2, 0.2]) and not info["fixed"].any()
+    part = fit_losvd._parinfo(x, 4, params=[10.0], fixed=[False, True], limitedmin=[True, False], maxpars=[100.0])
+    assert part["start"][0] == 10.0 and np.isnan(part["start"][1]) and list(part["start"][2:]) == [0.02, 0.02]
+    assert list(part["fixed"]) == [False, True, False, False]
+    assert part["lo"][0] == -490.0 and part["lo"][1] == -np.inf and part["lo"][2] == -0.2          # limitedmin[1] = False
+    assert part["hi"][0] == 100.0 and np.isclose(part["hi"][1], 980.0 / 3.0)
+    assert fit_losvd._set_ghparameters([1, 2, 3, 4, 5], [9] * 4, 4) == [1, 2, 3, 4]                 # longer lists are cut
+
+
+def test_shard_bounds_and_span_helpers():
+    from pynmap_b200 import sharded
+    for n, world in ((100, 3), (1_000_003, 8), (7, 8), (0, 2)):
+        cuts = [sharded.shard_bounds(n, r, world) for r in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:])) and all(lo <= hi for lo, hi in cuts)
+        assert all(lo % sharded.ALIGN == 0 for lo, _ in cuts[1:] if lo < n)
