@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, "libpnm_b200.so")
 SOURCES = ["pnm_api.cu", "pnm_host.cu"]
-HEADERS = ["pnm_common.cuh", "pnm_bin.cuh", "pnm_post.cuh", "pnm_fit.cuh", "pnm_profile.cuh",
+HEADERS = ["pnm_common.cuh", "pnm_bin.cuh", "pnm_post.cuh", "pnm_fit.cuh", "pnm_profile.cuh", "pnm_cube.cuh", "pnm_plan.cuh",
            os.path.join("..", "..", "include", "pnm_b200.h")]
 
 NVCC_FLAGS = [

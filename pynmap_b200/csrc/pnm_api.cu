@@ -11,6 +11,8 @@
 #include "pnm_post.cuh"
 #include "pnm_fit.cuh"
 #include "pnm_profile.cuh"
+#include "pnm_cube.cuh"
+#include "pnm_plan.cuh"
 
 namespace {
 
@@ -201,7 +203,7 @@ int pnm_grid_destroy(pnm_grid* g) {
 int64_t pnm_maps_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * PNM_MAP_SLOTS * g->replicas : 0; }
 int pnm_grid_map_replicas(const pnm_grid* g) { return g ? g->replicas : 0; }
 int64_t pnm_cube_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * g->nv : 0; }
-int64_t pnm_cube_moments_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * ((g->nv + 1) / 2) * 4 : 0; }
+int64_t pnm_cube_moments_acc_elems(const pnm_grid* g) { return g ? (int64_t)g->nx * g->ny * ((g->nv + 1) / 2 + 1) * 4 : 0; }
 
 }  // extern "C"
 
@@ -260,14 +262,14 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     if (acc_mode == PNM_ACC_FIXED && !scales3_host) return fail(PNM_EINVAL, "%s: FIXED mode needs scales", who);
     const int map_sums = sums & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2);
     if (!(sums & (PNM_SUM_W | PNM_SUM_WD | PNM_SUM_WD2 | PNM_SUM_CUBE))) return fail(PNM_EINVAL, "%s: no sums requested", who);
-    if (map_sums && !acc_maps) return fail(PNM_EINVAL, "%s: acc_maps is null", who);
+    if (map_sums && !acc_maps && !(sums & PNM_CUBE_MOMENTS)) return fail(PNM_EINVAL, "%s: acc_maps is null", who);
     if ((sums & PNM_SUM_CUBE) && (!acc_cube || g->nv < 1)) return fail(PNM_EINVAL, "%s: cube requested without cube accumulator / V axis", who);
     if ((sums & PNM_W_FROM_CUBE) && !((sums & PNM_SUM_CUBE) && (sums & PNM_SUM_W)))
         return fail(PNM_EINVAL, "%s: PNM_W_FROM_CUBE needs PNM_SUM_W|PNM_SUM_CUBE", who);
     if ((sums & PNM_CUBE_MOMENTS) &&
         (sums & (PNM_W_FROM_CUBE | PNM_SUM_WD | PNM_SUM_WD2)) != (PNM_W_FROM_CUBE | PNM_SUM_WD | PNM_SUM_WD2))
         return fail(PNM_EINVAL, "%s: PNM_CUBE_MOMENTS needs PNM_SUM_W|PNM_SUM_WD|PNM_SUM_WD2|PNM_SUM_CUBE|PNM_W_FROM_CUBE", who);
-    if ((sums & PNM_CUBE_MOMENTS) && (int64_t)g->nx * g->ny * ((g->nv + 1) / 2) * 4 >= (1LL << 31))
+    if ((sums & PNM_CUBE_MOMENTS) && pnm_cube_moments_acc_elems(g) >= (1LL << 31))
         return fail(PNM_ELIMIT, "%s: interleaved cube of 2^31 elements or more", who);
     if ((sums & (PNM_VAL_D32 | PNM_VAL_W32)) && (fused || dtype != PNM_F64))
         return fail(PNM_EINVAL, "%s: PNM_VAL_D32 / PNM_VAL_W32 describe float32 values carried as float64 (pnm_bin_points, PNM_F64)", who);
@@ -294,10 +296,10 @@ int bin_common(const char* who, bool fused, const pnm_grid* g, int64_t n, int dt
     const double* eps = dtype == PNM_F32 ? g->eps32 : g->eps64;
     p.eps_x = eps[0]; p.eps_y = eps[1]; p.eps_v = eps[2];
     p.sums = sums; p.nchain = fused ? nchain : 1; p.nviews = fused ? nviews : 1;
-    p.replicas = (sums & PNM_CUBE_MOMENTS) ? 1 : g->replicas;   // the maps only take the few particles outside the V range
+    p.replicas = (sums & PNM_CUBE_MOMENTS) ? 1 : g->replicas;   // (the interleaved cube does not use the maps accumulator)
     p.rep_shift = env_int("PNM_REP_SHIFT", 5);
     // hybrid scatter: 16-byte TMA bulk reductions need a 16-byte aligned maps accumulator
-    p.tma_slots = (acc_maps && (reinterpret_cast<uintptr_t>(acc_maps) & 15) == 0 && (sums & PNM_SUM_WD) && (sums & PNM_SUM_WD2))
+    p.tma_slots = (acc_maps && !(sums & PNM_CUBE_MOMENTS) && (reinterpret_cast<uintptr_t>(acc_maps) & 15) == 0 && (sums & PNM_SUM_WD) && (sums & PNM_SUM_WD2))
                       ? std::max(0, std::min(env_int("PNM_TMA_SLOTS", 0), pnm::kTmaSlots)) : 0;
     // (measured with lane-paired / lane-quad reductions, 1e8 particles: maps + cube 1.28 / 1.30 / 1.38 / 1.53 ms for
     //  0 / 2 / 3 / 4 of a tile's 8 updates through the TMA unit; maps only 0.86 / 0.88 ms for 0 / 2 -- a paired or quad
@@ -338,7 +340,7 @@ int pnm_bin_points(const pnm_grid* g, int64_t n, int dtype, const void* x, const
 int pnm_finalize_vmaps(const pnm_grid* g, const void* acc_maps, const void* acc_cube, int sums, int acc_mode,
                        const double* scales3_host, double* M, double* V, double* S, double* S1, double* S2,
                        void* stream) {
-    if (!g || !acc_maps) return fail(PNM_EINVAL, "pnm_finalize_vmaps: null grid / accumulator");
+    if (!g || (!acc_maps && !(sums & PNM_CUBE_MOMENTS))) return fail(PNM_EINVAL, "pnm_finalize_vmaps: null grid / accumulator");
     const int wfc = (sums & PNM_CUBE_MOMENTS) ? 2 : (sums & PNM_W_FROM_CUBE) ? 1 : 0;
     if (wfc && !acc_cube) return fail(PNM_EINVAL, "pnm_finalize_vmaps: PNM_W_FROM_CUBE without cube");
     const int npix = g->nx * g->ny;
@@ -610,6 +612,187 @@ int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* strea
     if (dtype == PNM_F32) pnm::k_absmax<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)a, n, (unsigned long long*)out_dev);
     else if (dtype == PNM_F64) pnm::k_absmax<double><<<grid, 256, 0, as_stream(stream)>>>((const double*)a, n, (unsigned long long*)out_dev);
     else return fail(PNM_EDTYPE, "pnm_absmax: dtype %d", dtype);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+// ------------------------------------------------------------------------------------ privatised scatter (pnm_cube.cuh)
+}  // extern "C"
+
+struct pnm_cube_plan {
+    int device;
+    int nx, ny, nv;
+    void* buf;                      // one allocation: [zeroed per build: colsum | rowsum | tot_len | tot_cap | voxhist] | rest
+    size_t zero_bytes;
+    pnm::CubePlan* plan;
+    pnm::PlanScratch s;
+    unsigned long long* work;       // chunk counter of k_project_cube
+    bool built;
+};
+
+namespace {
+
+float round_toward_zero_f32(double v) {
+    float f = (float)v;
+    if (std::fabs((double)f) > std::fabs(v)) f = nextafterf(f, 0.0f);
+    return f;
+}
+
+// the part of CubeParams that depends on the grid, the particles and the view
+int cube_params(const char* who, const pnm_grid* g, int64_t n, const float* x, const float* y, const float* z,
+                const float* vx, const float* vy, const float* vz, const float* w, const float* mat9_host,
+                pnm::CubeParams& p) {
+    if (!g) return fail(PNM_EINVAL, "%s: grid is null", who);
+    if (g->nv < 1) return fail(PNM_EINVAL, "%s: the grid has no V axis", who);
+    if (n < 0) return fail(PNM_EINVAL, "%s: n < 0", who);
+    if (!mat9_host) return fail(PNM_EINVAL, "%s: matrix is null", who);
+    if (n > 0 && (!x || !y || !z || !vx || !vy || !vz)) return fail(PNM_EINVAL, "%s: null particle array", who);
+    const void* ptrs[7] = {x, y, z, vx, vy, vz, w};
+    for (const void* q : ptrs)
+        if (reinterpret_cast<uintptr_t>(q) & 15) return fail(PNM_EINVAL, "%s: particle arrays must be 16-byte aligned", who);
+    if (pnm_cube_moments_acc_elems(g) >= (1LL << 31)) return fail(PNM_ELIMIT, "%s: interleaved cube of 2^31 elements or more", who);
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.x = x; p.y = y; p.z = z; p.vx = vx; p.vy = vy; p.vz = vz; p.w = w;
+    p.nx = g->nx; p.ny = g->ny; p.nv = g->nv; p.npix = g->nx * g->ny; p.G = (g->nv + 1) / 2;
+    p.ax = (float)g->inv_dx; p.cx = (float)(-g->x0 * g->inv_dx - 0.5); p.hx = round_toward_zero_f32(0.5 - g->eps32[0]);
+    p.ay = (float)g->inv_dy; p.cy = (float)(-g->y0 * g->inv_dy - 0.5); p.hy = round_toward_zero_f32(0.5 - g->eps32[1]);
+    p.av = (float)g->inv_dv; p.cv = (float)(-g->v0 * g->inv_dv - 0.5); p.hv = round_toward_zero_f32(0.5 - g->eps32[2]);
+    p.thr_x = g->thr32; p.thr_y = g->thr32 + g->nx + 1; p.thr_v = g->thr32 + g->nx + 1 + g->ny + 1;
+    memcpy(p.m, mat9_host, sizeof(p.m));
+    return PNM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t pnm_cube_slots_max(void) { return pnm::kCubeSlotsMax; }
+
+/* upper bound of the particles one CTA of k_project_cube can take: the bound behind the shared-memory fixed-point scale */
+int64_t pnm_cube_cta_terms(int64_t n) {
+    const int64_t nchunks = (n / 4 + 32 * pnm::kCubeSub - 1) / (32 * pnm::kCubeSub);
+    const int64_t cap = 2 * ((nchunks + pnm::kNumSMs - 1) / pnm::kNumSMs) + 2;
+    return cap * 128 * pnm::kCubeSub + 4;
+}
+
+int pnm_cube_plan_create(const pnm_grid* g, pnm_cube_plan** out) {
+    if (!out) return fail(PNM_EINVAL, "pnm_cube_plan_create: out is null");
+    *out = nullptr;
+    if (!g || g->nv < 1) return fail(PNM_EINVAL, "pnm_cube_plan_create: needs a grid with a V axis");
+    pnm_cube_plan* pl = new pnm_cube_plan();
+    pl->nx = g->nx; pl->ny = g->ny; pl->nv = g->nv; pl->built = false;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_col = up(sizeof(uint32_t) * g->nx), b_row = up(sizeof(uint32_t) * g->ny), b_tot = up(sizeof(uint32_t) * pnm::kPlanLevels);
+    const size_t b_sum = up(sizeof(double) * 4);
+    const size_t b_vox = up(sizeof(uint32_t) * (size_t)pnm::kBoxPix * g->nv);
+    const size_t b_keys = up(sizeof(uint2) * pnm::kPlanSample), b_lo = up(sizeof(uint16_t) * pnm::kBoxPix * pnm::kPlanLevels);
+    const size_t b_len = up((size_t)pnm::kBoxPix * pnm::kPlanLevels), b_cap = up(sizeof(uint32_t) * pnm::kBoxPix * pnm::kPlanLevels);
+    const size_t b_plan = up(sizeof(pnm::CubePlan)), b_work = 256;
+    pl->zero_bytes = b_col + b_row + 2 * b_tot + b_sum + b_vox;
+    const size_t total = pl->zero_bytes + b_keys + b_lo + b_len + b_cap + b_plan + b_work;
+    cudaError_t e = cudaGetDevice(&pl->device);
+    if (e == cudaSuccess) e = cudaMalloc(&pl->buf, total);
+    if (e == cudaSuccess) e = cudaMemset(pl->buf, 0, total);
+    if (e != cudaSuccess) { delete pl; return fail(PNM_ECUDA, "pnm_cube_plan_create: %s", cudaGetErrorString(e)); }
+    unsigned char* b = static_cast<unsigned char*>(pl->buf);
+    pl->s.colsum = reinterpret_cast<uint32_t*>(b); b += b_col;
+    pl->s.rowsum = reinterpret_cast<uint32_t*>(b); b += b_row;
+    pl->s.tot_len = reinterpret_cast<uint32_t*>(b); b += b_tot;
+    pl->s.tot_cap = reinterpret_cast<uint32_t*>(b); b += b_tot;
+    pl->s.sum_abs = reinterpret_cast<double*>(b); b += b_sum;
+    pl->s.voxhist = reinterpret_cast<uint32_t*>(b); b += b_vox;
+    pl->s.keys = reinterpret_cast<uint2*>(b); b += b_keys;
+    pl->s.lo = reinterpret_cast<uint16_t*>(b); b += b_lo;
+    pl->s.len = reinterpret_cast<uint8_t*>(b); b += b_len;
+    pl->s.cap = reinterpret_cast<uint32_t*>(b); b += b_cap;
+    pl->plan = reinterpret_cast<pnm::CubePlan*>(b); b += b_plan;
+    pl->work = reinterpret_cast<unsigned long long*>(b);
+    *out = pl;
+    return PNM_OK;
+}
+
+int pnm_cube_plan_destroy(pnm_cube_plan* pl) {
+    if (!pl) return PNM_OK;
+    cudaFree(pl->buf);
+    delete pl;
+    return PNM_OK;
+}
+
+int pnm_cube_plan_build(const pnm_grid* g, pnm_cube_plan* pl, int64_t n, const float* x, const float* y, const float* z,
+                        const float* vx, const float* vy, const float* vz, const float* w, const float* mat9_host, void* stream) {
+    if (!pl) return fail(PNM_EINVAL, "pnm_cube_plan_build: plan is null");
+    if (!g || g->nx != pl->nx || g->ny != pl->ny || g->nv != pl->nv) return fail(PNM_EINVAL, "pnm_cube_plan_build: the plan belongs to another grid");
+    pnm::CubeParams p;
+    const int rc = cube_params("pnm_cube_plan_build", g, n, x, y, z, vx, vy, vz, w, mat9_host, p);
+    if (rc != PNM_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    PNM_CUDA(cudaMemsetAsync(pl->buf, 0, pl->zero_bytes, st));
+    // groups of 8 consecutive particles, spread evenly over the snapshot
+    const int64_t groups = std::max<int64_t>(1, std::min<int64_t>(pnm::kPlanSample / 8, (n + 7) / 8));
+    const int64_t stride8 = std::max<int64_t>(8, ((n / groups) / 8) * 8);
+    const int64_t nsample = groups * 8;
+    pnm::k_plan_sample<<<grid_for(nsample, 256, 8), 256, 0, st>>>(p, pl->s, nsample, stride8);
+    pnm::k_plan_box<<<1, 1024, 0, st>>>(p, pl->s, pl->plan);
+    pnm::k_plan_vox<<<grid_for(nsample, 256, 8), 256, 0, st>>>(p, pl->s, pl->plan, nsample);
+    pnm::k_plan_levels<<<(pnm::kBoxPix * 32 + 255) / 256, 256, 0, st>>>(p, pl->s, pl->plan);
+    pnm::k_plan_finish<<<1, 1024, 0, st>>>(pl->s, pl->plan, pnm::kCubeSlotsMax, (int)nsample);
+    PNM_CUDA(cudaGetLastError());
+    pl->built = true;
+    return PNM_OK;
+}
+
+/* what the plan found (synchronises the stream): out8 = { bx0, by0, bw, bh, nslots, level, captured, sampled },
+ * mean3 = sample means of |w|, |w*d|, |w*d*d| */
+int pnm_cube_plan_info(const pnm_cube_plan* pl, int32_t* out8_host, double* mean3_host, void* stream) {
+    if (!pl || !out8_host || !mean3_host) return fail(PNM_EINVAL, "pnm_cube_plan_info: null argument");
+    if (!pl->built) return fail(PNM_EINVAL, "pnm_cube_plan_info: the plan has not been built");
+    PNM_CUDA(cudaMemcpyAsync(out8_host, pl->plan, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, as_stream(stream)));
+    PNM_CUDA(cudaMemcpyAsync(mean3_host, pl->plan->mean_abs, 3 * sizeof(double), cudaMemcpyDeviceToHost, as_stream(stream)));
+    PNM_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    return PNM_OK;
+}
+
+int pnm_project_cube(const pnm_grid* g, const pnm_cube_plan* pl, int64_t n, const float* x, const float* y, const float* z,
+                     const float* vx, const float* vy, const float* vz, const float* w, const float* mat9_host,
+                     int acc_mode, const double* scales3_host, const double* smem_scales3_host, void* acc_cube, void* stream) {
+    pnm::CubeParams p;
+    const int rc = cube_params("pnm_project_cube", g, n, x, y, z, vx, vy, vz, w, mat9_host, p);
+    if (rc != PNM_OK) return rc;
+    if (!pl || !pl->built) return fail(PNM_EINVAL, "pnm_project_cube: needs a built plan (pnm_cube_plan_build)");
+    if (g->nx != pl->nx || g->ny != pl->ny || g->nv != pl->nv) return fail(PNM_EINVAL, "pnm_project_cube: the plan belongs to another grid");
+    if (!acc_cube) return fail(PNM_EINVAL, "pnm_project_cube: acc_cube is null");
+    if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_project_cube: acc_mode %d", acc_mode);
+    if (acc_mode == PNM_ACC_FIXED && !scales3_host) return fail(PNM_EINVAL, "pnm_project_cube: FIXED mode needs scales");
+    if (acc_mode == PNM_ACC_F64 && !smem_scales3_host) return fail(PNM_EINVAL, "pnm_project_cube: float64 mode needs the shared-memory scales");
+    if (n == 0) return PNM_OK;
+    for (int k = 0; k < 3; ++k) {
+        const double sg = acc_mode == PNM_ACC_FIXED ? scales3_host[k] : 1.0;
+        const double ss = acc_mode == PNM_ACC_FIXED ? scales3_host[k] : smem_scales3_host[k];
+        int e = 0;
+        // powers of two inside the float32 exponent range (the kernel scales in float32, see to_fix)
+        if (!(ss > 0.0) || std::frexp(ss, &e) != 0.5 || e < -119 || e > 121 || std::frexp(sg, &e) != 0.5 || e < -119 || e > 121)
+            return fail(PNM_EINVAL, "pnm_project_cube: scales must be powers of two between 2^-120 and 2^120");
+        p.sc_glob[k] = (float)sg; p.sc_smem[k] = (float)ss;
+        p.inv_smem[k] = 1.0 / ss;
+    }
+    p.cube = acc_cube; p.plan = pl->plan; p.work = pl->work;
+    const int64_t nchunks = (n / 4 + 32 * pnm::kCubeSub - 1) / (32 * pnm::kCubeSub);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(pnm::kNumSMs, (nchunks + pnm::kCubeWarps - 1) / pnm::kCubeWarps));
+    p.cta_cap = (int)std::min<int64_t>(0x7fffffff, 2 * ((nchunks + pnm::kNumSMs - 1) / pnm::kNumSMs) + 2);
+#ifdef PNM_CUBE_KNOBS
+    p.dbg = env_int("PNM_CUBE_DBG", 0);
+#endif
+    cudaStream_t st = as_stream(stream);
+    PNM_CUDA(cudaMemsetAsync(pl->work, 0, sizeof(unsigned long long), st));
+#define PNM_LAUNCH_CUBE(ACC, HW)                                                                                    \
+    do {                                                                                                            \
+        auto kern = pnm::k_project_cube<ACC, HW>;                                                                   \
+        PNM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, pnm::kCubeSmemBytes));     \
+        kern<<<grid, pnm::kCubeThreads, pnm::kCubeSmemBytes, st>>>(p);                                              \
+    } while (0)
+    if (acc_mode == PNM_ACC_F64) { if (w) PNM_LAUNCH_CUBE(PNM_ACC_F64, true); else PNM_LAUNCH_CUBE(PNM_ACC_F64, false); }
+    else { if (w) PNM_LAUNCH_CUBE(PNM_ACC_FIXED, true); else PNM_LAUNCH_CUBE(PNM_ACC_FIXED, false); }
+#undef PNM_LAUNCH_CUBE
     PNM_CUDA(cudaGetLastError());
     return PNM_OK;
 }

@@ -118,14 +118,13 @@ __device__ __forceinline__ int guess_bin(T x, const Axis<T>& a, bool& sure) {
 template <int ACC> struct AccT { using type = double; };
 template <> struct AccT<PNM_ACC_FIXED> { using type = long long; };
 
-// FIXED: rint(value * 2^k); the product with a power of two is exact in the particle dtype, so
-// the float32 path needs no widening.  Non-finite values quantise to 0 (documented deviation: the
+// FIXED: rint(value * 2^k), the product formed in float64 (exact: a power of two).  Non-finite values quantise to 0 (documented deviation: the
 // float64 path propagates NaN like the reference does).
 template <int ACC>
 __device__ __forceinline__ typename AccT<ACC>::type to_acc(float v, double scale) {
     if (ACC == PNM_ACC_F64) return (typename AccT<ACC>::type)v;
-    const float s = v * (float)scale;
-    return (typename AccT<ACC>::type)(is_finite(s) ? __float2ll_rn(s) : 0ll);
+    const double s = (double)v * scale;            // (float)scale would overflow for 2^k with k > 127
+    return (typename AccT<ACC>::type)(is_finite(s) ? __double2ll_rn(s) : 0ll);
 }
 template <int ACC>
 __device__ __forceinline__ typename AccT<ACC>::type to_acc(double v, double scale) {
@@ -377,22 +376,18 @@ struct Binner {
         if ((unsigned)ix >= (unsigned)nx || (unsigned)iy >= (unsigned)ny) return;
         const bool in_v = want_v && (unsigned)iv < (unsigned)av.n;
         if (sm & PNM_CUBE_MOMENTS) {
-            // interleaved cube: record (iv / 2, pixel) = { w of the even bin, w of the odd bin, sum w*d, sum w*d*d }.
-            // A particle inside the V range touches ONE sector; outside it, its three sums go to the (remainder) maps.
+            // interleaved cube: record (iv / 2, pixel) = { w of the even bin, w of the odd bin, sum w*d, sum w*d*d };
+            // a particle outside the V range goes to slot 0 of the extra record slab G = ceil(nv / 2).  Every particle
+            // touches ONE sector and the maps accumulator is not used at all.
             T wd, wdd;
             weighted_terms(sm, w, d, wd, wdd);
             const A aw = to_acc<ACC>(w, sc0), a1 = to_acc<ACC>(wd, sc1), a2 = to_acc<ACC>(wdd, sc2);
-            if (in_v) {
-                const int coff = ((iv >> 1) * npix + ix * ny + iy) * 4;
-                if (PNM_PAIRED && mom) {
-                    mom->off = coff | (iv & 1); mom->w = aw; mom->s1 = a1; mom->s2 = a2;
-                } else {
-                    red_add(cube + coff + (iv & 1), aw); red_add(cube + coff + 2, a1); red_add(cube + coff + 3, a2);
-                }
-            } else if (PNM_PAIRED && prev) {
-                prev->off = (iy * nx + ix) * PNM_MAP_SLOTS; prev->s0 = aw; prev->s1 = a1; prev->s2 = a2; prev->has0 = true;
+            const int ivp = in_v ? iv : 2 * ((av.n + 1) >> 1);
+            const int coff = ((ivp >> 1) * npix + ix * ny + iy) * 4;
+            if (PNM_PAIRED && mom) {
+                mom->off = coff | (ivp & 1); mom->w = aw; mom->s1 = a1; mom->s2 = a2;
             } else {
-                run.add(maps, sm, st, (iy * nx + ix) * PNM_MAP_SLOTS, true, aw, a1, a2);
+                red_add(cube + coff + (ivp & 1), aw); red_add(cube + coff + 2, a1); red_add(cube + coff + 3, a2);
             }
             return;
         }
@@ -552,7 +547,6 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
 #pragma unroll
                     for (int k = 0; k < VN; ++k) {
                         CubeRec<ACC> rec;
-                        MapRun<ACC> rem;                   // a particle outside the V range: its sums go to the maps
                         if (live) {
                             T px = x[k], py = y[k], d = vx[k];
                             if (FUSED) {
@@ -560,12 +554,10 @@ __global__ void __launch_bounds__(kBinThreads, PNM_MINBLOCKS) k_project_bin(cons
                                 py = rot_row(m[3], m[4], m[5], x[k], y[k], z[k]);
                                 d = rot_row(m[6], m[7], m[8], vx[k], vy[k], vz[k]);
                             }
-                            bool due = false;
-                            B.scatter(maps0, cube0, run, st, px, py, d, W ? w[k] : (T)1, false, &rem, &due, &rec);
+                            B.scatter(maps0, cube0, run, st, px, py, d, W ? w[k] : (T)1, false, nullptr, nullptr, &rec);
                         }
                         // three lanes per particle: lane 0 sends w to its velocity bin, lanes 2 and 3 the two moments
                         quad_reduce<A, true>(cube0, rec.off, rec.w, A(0), rec.s1, rec.s2, lane, 13);
-                        if (__any_sync(0xffffffffu, rem.off >= 0)) rem.flush_quad(maps0, B.sums(), lane);
                     }
                 } else
 #pragma unroll

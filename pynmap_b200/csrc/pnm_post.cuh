@@ -58,9 +58,10 @@ __global__ void __launch_bounds__(256) k_finalize_vmaps(const void* acc_maps, co
     const int npix = nx * ny;
     A t = 0, t1 = 0, t2 = 0;
     if (w_from_cube == 2 && q < npix) {
-        // interleaved cube (PNM_CUBE_MOMENTS): records [g][q] = { w even, w odd, sum w*d, sum w*d*d }
+        // interleaved cube (PNM_CUBE_MOMENTS): records [g][q] = { w even, w odd, sum w*d, sum w*d*d }, g <= G;
+        // record slab G = ceil(nv / 2) holds the particles outside the V range
         const A* c = reinterpret_cast<const A*>(acc_cube);
-        for (int g = threadIdx.y; g < (nv + 1) / 2; g += 8) {
+        for (int g = threadIdx.y; g <= (nv + 1) / 2; g += 8) {
             const A* rec = c + ((int64_t)g * npix + q) * 4;
             t += rec[0] + rec[1]; t1 += rec[2]; t2 += rec[3];
         }
@@ -76,14 +77,8 @@ __global__ void __launch_bounds__(256) k_finalize_vmaps(const void* acc_maps, co
     const int pix = iy * nx + ix;                            // map layout [iy][ix] (the reference's .T)
     double s0;
     if (w_from_cube == 2) {
-        // all three sums = what the particles outside the V range left in the maps + the V-sums of the cube records
-        const A* m = reinterpret_cast<const A*>(acc_maps);
-        const int64_t stride = (int64_t)npix * PNM_MAP_SLOTS;
+        // all three sums = V-sums of the cube records (the maps accumulator is not used with this layout)
         A tot0 = 0, tot1 = 0, tot2 = 0;
-        for (int r = 0; r < replicas; ++r) {
-            const A* rec = m + r * stride + (int64_t)pix * PNM_MAP_SLOTS;
-            tot0 += rec[kSlotS0]; tot1 += rec[kSlotS1]; tot2 += rec[kSlotS2];
-        }
         for (int k = 0; k < 8; ++k) { tot0 += part[k][threadIdx.x]; tot1 += part1[k][threadIdx.x]; tot2 += part2[k][threadIdx.x]; }
         const double s0m = (ACC == PNM_ACC_F64) ? (double)tot0 : __dmul_rn((double)tot0, is0);
         const double s1m = (ACC == PNM_ACC_F64) ? (double)tot1 : __dmul_rn((double)tot1, is1);

@@ -134,8 +134,9 @@ class Grid(object):
 
     @property
     def cube_moments_elems(self):
-        """Interleaved cube (CUBE_MOMENTS): records {w even bin, w odd bin, sum w*d, sum w*d*d} per (iv // 2, pixel)."""
-        return self.nx * self.ny * ((self.nv + 1) // 2) * 4
+        """Interleaved cube (CUBE_MOMENTS): records {w even bin, w odd bin, sum w*d, sum w*d*d} per (iv // 2, pixel),
+        plus one record slab for the particles outside the V range."""
+        return self.nx * self.ny * ((self.nv + 1) // 2 + 1) * 4
 
     def centres(self):
         """Pixel centres (grid.py:141-142, :247-249); fresh arrays, the caller may keep them."""
@@ -305,6 +306,89 @@ def _project_bin_call(grid, x, soa, w, mats, nchain, nviews, sums, acc, scales, 
               ptr(w), ptr(mask), mask_mode,
               mats.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), nchain, nviews,
               sums, acc.code, _scales_arg(acc, scales), ptr(maps), ptr(cube), stream_ptr())
+
+
+class CubePlan(object):
+    """pnm_cube_plan handle: which pixels' moments and which voxels' weights k_project_cube accumulates in shared
+    memory first (csrc/pnm_cube.cuh, csrc/pnm_plan.cuh).  Built on the device from a sample of the particles; it
+    changes the speed of project_cube, never its result."""
+
+    def __init__(self, grid):
+        self.grid = grid
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(grid.device):
+            _lib.call("pnm_cube_plan_create", grid.handle, ctypes.byref(self.handle))
+
+    def build(self, soa, w, mat):
+        m = np.ascontiguousarray(np.asarray(mat, dtype=np.float32).reshape(9))
+        _lib.call("pnm_cube_plan_build", self.grid.handle, self.handle, soa[0].numel(),
+                  ptr(soa[0]), ptr(soa[1]), ptr(soa[2]), ptr(soa[3]), ptr(soa[4]), ptr(soa[5]), ptr(w),
+                  m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), stream_ptr())
+        self._info = None
+        return self
+
+    def info(self):
+        """dict(bx0, by0, bw, bh, nslots, level, captured, sampled, mean_abs=(|w|, |w d|, |w d d|)) of the last
+        build -- one stream synchronisation, then cached."""
+        if getattr(self, "_info", None) is None:
+            out, mean = (ctypes.c_int32 * 8)(), (ctypes.c_double * 3)()
+            _lib.call("pnm_cube_plan_info", self.handle, out, mean, stream_ptr())
+            self._info = dict(zip(("bx0", "by0", "bw", "bh", "nslots", "level", "captured", "sampled"), [int(v) for v in out]))
+            self._info["mean_abs"] = tuple(float(v) for v in mean)
+        return self._info
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().pnm_cube_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+CUBE_TYPICAL_FACTOR = 8.0     # terms up to this many times the sample mean fit the low 32-bit limb
+
+
+def cube_smem_scales(n, max_w, max_d, mean_abs=None):
+    """Power-of-two fixed-point scales 2^k of the shared-memory sums of k_project_cube under float64 accumulation.
+    Two caps: (a) no overflow -- one CTA adds at most pnm_cube_cta_terms(n) terms to a sum, so
+    2^k * terms * max|term| <= 2^62; (b) speed -- terms up to CUBE_TYPICAL_FACTOR x the sample mean of |term| fit the
+    low 32-bit limb (2^k * 8 mean <= 2^31), so that the high limb only takes carries and the rare large term.  The
+    privatised terms are therefore rounded to multiples of 2^-k ~ 3.7e-9 x the mean |term| (each float32 product the
+    reference forms already carries a rounding of 6e-8 of ITS size).  k is kept inside +-120: the kernel scales in
+    float32."""
+    out = fixed_scales(int(_lib.load().pnm_cube_cta_terms(int(n))), max_w, max_d)
+    if mean_abs is not None:
+        for k, m in enumerate(mean_abs):
+            if m > 0.0 and math.isfinite(m):
+                out[k] = min(out[k], math.ldexp(1.0, int(math.floor(31 - math.log2(CUBE_TYPICAL_FACTOR * m)))))
+    return [min(max(s, 2.0 ** -120), 2.0 ** 120) for s in out]
+
+
+def cube_scales_ok(scales):
+    """True when int64 fixed-point scales can be applied in float32 (project_cube), i.e. 2^-120 <= 2^k <= 2^120."""
+    return scales is None or all(2.0 ** -120 <= float(s) <= 2.0 ** 120 for s in scales)
+
+
+def project_cube(grid, plan, soa, w, mat, acc, scales, smem_scales, cube):
+    """pnm_project_cube: float32 SoA particles, one view; adds into the interleaved cube accumulator ``cube``
+    (grid.cube_moments_elems elements of acc.dtype)."""
+    x = soa[0]
+    if x.dtype != torch.float32:
+        raise TypeError("project_cube takes float32 particles")
+    m = np.ascontiguousarray(np.asarray(mat, dtype=np.float32).reshape(9))
+    args = (grid.handle, plan.handle, x.numel(), ptr(soa[0]), ptr(soa[1]), ptr(soa[2]), ptr(soa[3]), ptr(soa[4]),
+            ptr(soa[5]), ptr(w), m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), acc.code,
+            _scales_arg(acc, scales), _lib.doubles(smem_scales) if smem_scales is not None else None,
+            ptr(cube), stream_ptr())
+    if KERNEL_TIMER is not None:
+        t0, t1 = KERNEL_TIMER.bracket()
+        t0.record()
+        try:
+            _lib.call("pnm_project_cube", *args)
+        finally:
+            t1.record()
+        return
+    _lib.call("pnm_project_cube", *args)
 
 
 def bin_points(grid, x, y, d, w, sums, acc, scales, maps, cube, mask=None, mask_mode=0):
