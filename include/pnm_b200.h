@@ -20,6 +20,8 @@
  *   pnm_amr_jitter/repeat spread_amr                           pynmap/misc_io.py:184-224
  *   pnm_fit_gh            fitgh (mpfit) per spaxel             pynmap/losvd.py:53-67, fit_losvd.py:57-235
  *   pnm_absmax            (new) bound for the fixed-point scale
+ *   pnm_project_cube      pnm_project_bin for the hot configuration (float32 particles, one view, maps + cube),
+ *   pnm_cube_plan_*       hot pixels / voxels accumulated in shared memory first (same sums, same layout)
  *   pnm_project_host      snapshot.rotate + velocity_moments + create_losvds from HOST arrays
  *                                                              pynmap/pynmap.py:246-285, :319-340, :439-455
  *
@@ -126,7 +128,7 @@ int pnm_grid_destroy(pnm_grid* g);
  * at finalisation, the cube accumulator is velocity-major.  Sizes per view, in 8-byte elements:  */
 int64_t pnm_maps_acc_elems(const pnm_grid* g); /* replicas*ny*nx*PNM_MAP_SLOTS */
 int64_t pnm_cube_acc_elems(const pnm_grid* g); /* nx*ny*nv                     */
-int64_t pnm_cube_moments_acc_elems(const pnm_grid* g); /* ceil(nv/2)*nx*ny*4 with PNM_CUBE_MOMENTS */
+int64_t pnm_cube_moments_acc_elems(const pnm_grid* g); /* (ceil(nv/2)+1)*nx*ny*4 with PNM_CUBE_MOMENTS */
 int pnm_grid_map_replicas(const pnm_grid* g);
 /* Sums the map replicas into the first one, so that a multi-GPU reduction only has to move the
  * first ny*nx*PNM_MAP_SLOTS elements.  clear_others != 0 also zeroes replicas 1.. (the buffer can
@@ -265,6 +267,36 @@ int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t
 
 /* ---- max |a[i]| over n elements -> out_dev[0] (float64, device); used to pick FIXED scales -- */
 int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream);
+
+/* ---- privatised scatter: pnm_project_bin(sums = W|WD|WD2|CUBE|W_FROM_CUBE|CUBE_MOMENTS) for float32 particles, one
+ * view, one matrix, no mask (rotation.py:115-117 + grid.py:126-131 + grid.py:252-259 in one read of the particles).
+ * Same accumulator (pnm_cube_moments_acc_elems elements, PNM_CUBE_MOMENTS layout; the maps accumulator is not used),
+ * same finalisers.  Every CTA first accumulates, in shared memory, sum w*d and sum w*d*d of the pixels of a box of at
+ * most 64 x 64 pixels and sum w of the most populated voxels of that box; what to keep there is decided by a PLAN built
+ * on the device from a sample of the particles (pnm_cube_plan_build; rebuild it when the snapshot, the view or the
+ * grid changes -- a stale plan only costs speed, never correctness).
+ *   PNM_ACC_FIXED: bit-identical to pnm_project_bin with the same scales for any plan.  scales3_host must be powers
+ *                  of two in [2^-120, 2^120]; a term stays in shared memory only while |term * 2^k| < 2^31, so scales
+ *                  that put the typical term near 2^23 (pnm_cube_plan_info reports such scales) are the fast ones.
+ *   PNM_ACC_F64  : privatised terms are rounded to 2^-24 of the sample mean of |term| (weights below 1/16 of the
+ *                  typical one, terms above 128 x the typical one and non-finite terms take the exact RED path):
+ *                  per-voxel / per-pixel sums agree with pnm_project_bin to better than 5e-7 relative.
+ * Particle arrays must be 16-byte aligned; n < 2^32.  Launches that share a plan must be ordered on one stream (the
+ * plan owns the kernel's work counter).
+ *   pnm_cube_plan_info (synchronises `stream`): out8_host = { box x0, y0, width, height, voxel slots used, threshold
+ *   level, sample particles captured, sample size }; stats6_host = sample means of |w|, |w*d|, |w*d*d| and the 2^k
+ *   the float64 mode applies to them.                                                                        */
+typedef struct pnm_cube_plan pnm_cube_plan;
+int32_t pnm_cube_slots_max(void);
+int pnm_cube_plan_create(const pnm_grid* g, pnm_cube_plan** out);
+int pnm_cube_plan_destroy(pnm_cube_plan* plan);
+int pnm_cube_plan_build(const pnm_grid* g, pnm_cube_plan* plan, int64_t n, const float* x, const float* y, const float* z,
+                        const float* vx, const float* vy, const float* vz, const float* w, const float* mat9_host,
+                        void* stream);
+int pnm_cube_plan_info(const pnm_cube_plan* plan, int32_t* out8_host, double* stats6_host, void* stream);
+int pnm_project_cube(const pnm_grid* g, const pnm_cube_plan* plan, int64_t n, const float* x, const float* y,
+                     const float* z, const float* vx, const float* vy, const float* vz, const float* w,
+                     const float* mat9_host, int acc_mode, const double* scales3_host, void* acc_cube, void* stream);
 
 /* ---- host-buffer path: what a reference user calls, end to end -------------------------------
  * Particle arrays live in HOST memory (pinned or pageable).  pnm_accumulate_host streams them

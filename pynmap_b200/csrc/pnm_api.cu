@@ -668,13 +668,6 @@ extern "C" {
 
 int32_t pnm_cube_slots_max(void) { return pnm::kCubeSlotsMax; }
 
-/* upper bound of the particles one CTA of k_project_cube can take: the bound behind the shared-memory fixed-point scale */
-int64_t pnm_cube_cta_terms(int64_t n) {
-    const int64_t nchunks = (n / 4 + 32 * pnm::kCubeSub - 1) / (32 * pnm::kCubeSub);
-    const int64_t cap = 2 * ((nchunks + pnm::kNumSMs - 1) / pnm::kNumSMs) + 2;
-    return cap * 128 * pnm::kCubeSub + 4;
-}
-
 int pnm_cube_plan_create(const pnm_grid* g, pnm_cube_plan** out) {
     if (!out) return fail(PNM_EINVAL, "pnm_cube_plan_create: out is null");
     *out = nullptr;
@@ -742,19 +735,22 @@ int pnm_cube_plan_build(const pnm_grid* g, pnm_cube_plan* pl, int64_t n, const f
 }
 
 /* what the plan found (synchronises the stream): out8 = { bx0, by0, bw, bh, nslots, level, captured, sampled },
- * mean3 = sample means of |w|, |w*d|, |w*d*d| */
-int pnm_cube_plan_info(const pnm_cube_plan* pl, int32_t* out8_host, double* mean3_host, void* stream) {
-    if (!pl || !out8_host || !mean3_host) return fail(PNM_EINVAL, "pnm_cube_plan_info: null argument");
+ * stats6 = sample means of |w|, |w*d|, |w*d*d|, then the 2^k the float64 mode scales them with in shared memory */
+int pnm_cube_plan_info(const pnm_cube_plan* pl, int32_t* out8_host, double* stats6_host, void* stream) {
+    if (!pl || !out8_host || !stats6_host) return fail(PNM_EINVAL, "pnm_cube_plan_info: null argument");
     if (!pl->built) return fail(PNM_EINVAL, "pnm_cube_plan_info: the plan has not been built");
+    float sc[3];
     PNM_CUDA(cudaMemcpyAsync(out8_host, pl->plan, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, as_stream(stream)));
-    PNM_CUDA(cudaMemcpyAsync(mean3_host, pl->plan->mean_abs, 3 * sizeof(double), cudaMemcpyDeviceToHost, as_stream(stream)));
+    PNM_CUDA(cudaMemcpyAsync(stats6_host, pl->plan->mean_abs, 3 * sizeof(double), cudaMemcpyDeviceToHost, as_stream(stream)));
+    PNM_CUDA(cudaMemcpyAsync(sc, pl->plan->sc_smem, 3 * sizeof(float), cudaMemcpyDeviceToHost, as_stream(stream)));
     PNM_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    for (int k = 0; k < 3; ++k) stats6_host[3 + k] = (double)sc[k];
     return PNM_OK;
 }
 
 int pnm_project_cube(const pnm_grid* g, const pnm_cube_plan* pl, int64_t n, const float* x, const float* y, const float* z,
                      const float* vx, const float* vy, const float* vz, const float* w, const float* mat9_host,
-                     int acc_mode, const double* scales3_host, const double* smem_scales3_host, void* acc_cube, void* stream) {
+                     int acc_mode, const double* scales3_host, void* acc_cube, void* stream) {
     pnm::CubeParams p;
     const int rc = cube_params("pnm_project_cube", g, n, x, y, z, vx, vy, vz, w, mat9_host, p);
     if (rc != PNM_OK) return rc;
@@ -763,22 +759,19 @@ int pnm_project_cube(const pnm_grid* g, const pnm_cube_plan* pl, int64_t n, cons
     if (!acc_cube) return fail(PNM_EINVAL, "pnm_project_cube: acc_cube is null");
     if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_project_cube: acc_mode %d", acc_mode);
     if (acc_mode == PNM_ACC_FIXED && !scales3_host) return fail(PNM_EINVAL, "pnm_project_cube: FIXED mode needs scales");
-    if (acc_mode == PNM_ACC_F64 && !smem_scales3_host) return fail(PNM_EINVAL, "pnm_project_cube: float64 mode needs the shared-memory scales");
+    if (n >= (1LL << 32)) return fail(PNM_ELIMIT, "pnm_project_cube: 2^32 particles or more in one call");   // carries of one CTA fit the signed high limb
     if (n == 0) return PNM_OK;
     for (int k = 0; k < 3; ++k) {
         const double sg = acc_mode == PNM_ACC_FIXED ? scales3_host[k] : 1.0;
-        const double ss = acc_mode == PNM_ACC_FIXED ? scales3_host[k] : smem_scales3_host[k];
         int e = 0;
-        // powers of two inside the float32 exponent range (the kernel scales in float32, see to_fix)
-        if (!(ss > 0.0) || std::frexp(ss, &e) != 0.5 || e < -119 || e > 121 || std::frexp(sg, &e) != 0.5 || e < -119 || e > 121)
+        // powers of two inside the float32 exponent range (the kernel scales in float32, see to_acc_f)
+        if (!(sg > 0.0) || std::frexp(sg, &e) != 0.5 || e < -119 || e > 121)
             return fail(PNM_EINVAL, "pnm_project_cube: scales must be powers of two between 2^-120 and 2^120");
-        p.sc_glob[k] = (float)sg; p.sc_smem[k] = (float)ss;
-        p.inv_smem[k] = 1.0 / ss;
+        p.sc_glob[k] = (float)sg;
     }
     p.cube = acc_cube; p.plan = pl->plan; p.work = pl->work;
-    const int64_t nchunks = (n / 4 + 32 * pnm::kCubeSub - 1) / (32 * pnm::kCubeSub);
+    const int64_t nchunks = (n + pnm::kCubeChunk - 1) / pnm::kCubeChunk;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(pnm::kNumSMs, (nchunks + pnm::kCubeWarps - 1) / pnm::kCubeWarps));
-    p.cta_cap = (int)std::min<int64_t>(0x7fffffff, 2 * ((nchunks + pnm::kNumSMs - 1) / pnm::kNumSMs) + 2);
 #ifdef PNM_CUBE_KNOBS
     p.dbg = env_int("PNM_CUBE_DBG", 0);
 #endif

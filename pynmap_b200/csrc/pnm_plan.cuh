@@ -175,7 +175,16 @@ __global__ void __launch_bounds__(1024) k_plan_finish(PlanScratch s, CubePlan* p
         plan->captured = (int)s.tot_cap[level];
         plan->sampled = nsample;
         const double cnt = s.sum_abs[3] > 0.0 ? s.sum_abs[3] : 1.0;
-        for (int k = 0; k < 3; ++k) plan->mean_abs[k] = s.sum_abs[k] / cnt;
+        for (int k = 0; k < 3; ++k) {
+            const double m = s.sum_abs[k] / cnt;
+            plan->mean_abs[k] = m;
+            // float64 accumulators: 2^k that puts the mean |term| into [2^kCubeTypBits, 2^(kCubeTypBits+1)); applied in float32
+            int e = 0;
+            if (m > 0.0 && m <= 1.7976931348623157e+308) e = ilogb(m);
+            const int kk = max(-120, min(120, kCubeTypBits - e));
+            plan->sc_smem[k] = (float)ldexp(1.0, kk);
+            plan->inv_smem[k] = ldexp(1.0, -kk);
+        }
     }
 }
 

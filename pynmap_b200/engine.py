@@ -328,13 +328,14 @@ class CubePlan(object):
         return self
 
     def info(self):
-        """dict(bx0, by0, bw, bh, nslots, level, captured, sampled, mean_abs=(|w|, |w d|, |w d d|)) of the last
-        build -- one stream synchronisation, then cached."""
+        """dict(bx0, by0, bw, bh, nslots, level, captured, sampled, mean_abs=(|w|, |w d|, |w d d|), smem_scales) of
+        the last build -- one stream synchronisation, then cached."""
         if getattr(self, "_info", None) is None:
-            out, mean = (ctypes.c_int32 * 8)(), (ctypes.c_double * 3)()
-            _lib.call("pnm_cube_plan_info", self.handle, out, mean, stream_ptr())
+            out, stats = (ctypes.c_int32 * 8)(), (ctypes.c_double * 6)()
+            _lib.call("pnm_cube_plan_info", self.handle, out, stats, stream_ptr())
             self._info = dict(zip(("bx0", "by0", "bw", "bh", "nslots", "level", "captured", "sampled"), [int(v) for v in out]))
-            self._info["mean_abs"] = tuple(float(v) for v in mean)
+            self._info["mean_abs"] = tuple(float(v) for v in stats[:3])
+            self._info["smem_scales"] = tuple(float(v) for v in stats[3:])
         return self._info
 
     def __del__(self):
@@ -345,22 +346,18 @@ class CubePlan(object):
             pass
 
 
-CUBE_TYPICAL_FACTOR = 8.0     # terms up to this many times the sample mean fit the low 32-bit limb
+CUBE_TYP_BITS = 23            # csrc/pnm_cube.cuh kCubeTypBits
 
 
-def cube_smem_scales(n, max_w, max_d, mean_abs=None):
-    """Power-of-two fixed-point scales 2^k of the shared-memory sums of k_project_cube under float64 accumulation.
-    Two caps: (a) no overflow -- one CTA adds at most pnm_cube_cta_terms(n) terms to a sum, so
-    2^k * terms * max|term| <= 2^62; (b) speed -- terms up to CUBE_TYPICAL_FACTOR x the sample mean of |term| fit the
-    low 32-bit limb (2^k * 8 mean <= 2^31), so that the high limb only takes carries and the rare large term.  The
-    privatised terms are therefore rounded to multiples of 2^-k ~ 3.7e-9 x the mean |term| (each float32 product the
-    reference forms already carries a rounding of 6e-8 of ITS size).  k is kept inside +-120: the kernel scales in
-    float32."""
-    out = fixed_scales(int(_lib.load().pnm_cube_cta_terms(int(n))), max_w, max_d)
-    if mean_abs is not None:
-        for k, m in enumerate(mean_abs):
-            if m > 0.0 and math.isfinite(m):
-                out[k] = min(out[k], math.ldexp(1.0, int(math.floor(31 - math.log2(CUBE_TYPICAL_FACTOR * m)))))
+def cube_fixed_scales(n_total, max_w, max_d, mean_abs):
+    """int64 fixed-point scales for runs through k_project_cube: engine.fixed_scales (no overflow for n_total
+    worst-case terms), capped so that the typical term (the plan's sample mean of |term|) lands in [2^23, 2^24) --
+    the kernel keeps a term in shared memory only when its scaled value fits 32 bits.  The cap trades resolution
+    (2^-24 of the typical term instead of ~2^-36) for speed; any power of two gives bit-exact, order-independent sums."""
+    out = fixed_scales(n_total, max_w, max_d)
+    for k, m in enumerate(mean_abs):
+        if m > 0.0 and math.isfinite(m):
+            out[k] = min(out[k], math.ldexp(1.0, CUBE_TYP_BITS - int(math.floor(math.log2(m)))))
     return [min(max(s, 2.0 ** -120), 2.0 ** 120) for s in out]
 
 
@@ -369,17 +366,24 @@ def cube_scales_ok(scales):
     return scales is None or all(2.0 ** -120 <= float(s) <= 2.0 ** 120 for s in scales)
 
 
-def project_cube(grid, plan, soa, w, mat, acc, scales, smem_scales, cube):
+def cube_path_ok(grid, soa, w):
+    """k_project_cube takes float32 particles whose arrays are 16-byte aligned, and a grid with a V axis."""
+    if grid.nv < 1 or soa[0].dtype != torch.float32 or grid.cube_moments_elems >= 2 ** 31 or soa[0].numel() >= 2 ** 32:
+        return False
+    return all(t is None or t.data_ptr() % 16 == 0 for t in tuple(soa) + (w,))
+
+
+def project_cube(grid, plan, soa, w, mat, acc, scales, cube):
     """pnm_project_cube: float32 SoA particles, one view; adds into the interleaved cube accumulator ``cube``
-    (grid.cube_moments_elems elements of acc.dtype)."""
+    (grid.cube_moments_elems elements of acc.dtype).  Launches that share a plan must share a stream (the plan
+    owns the kernel's work counter)."""
     x = soa[0]
     if x.dtype != torch.float32:
         raise TypeError("project_cube takes float32 particles")
     m = np.ascontiguousarray(np.asarray(mat, dtype=np.float32).reshape(9))
     args = (grid.handle, plan.handle, x.numel(), ptr(soa[0]), ptr(soa[1]), ptr(soa[2]), ptr(soa[3]), ptr(soa[4]),
             ptr(soa[5]), ptr(w), m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), acc.code,
-            _scales_arg(acc, scales), _lib.doubles(smem_scales) if smem_scales is not None else None,
-            ptr(cube), stream_ptr())
+            _scales_arg(acc, scales), ptr(cube), stream_ptr())
     if KERNEL_TIMER is not None:
         t0, t1 = KERNEL_TIMER.bracket()
         t0.record()

@@ -23,12 +23,12 @@ mat = rotation.rotation_matrix(np.float32(30), np.float32(60))
 grid = engine.get_grid(workloads.LIM_XY, nxy, nxy, workloads.LIM_V, nv)
 f64, fx = engine.AccMode("f64"), engine.AccMode("fixed")
 max_w, max_d = engine.absmax(w), max(engine.absmax(r) for r in rows[3:6]) * 3 ** 0.5
-scales = engine.fixed_scales(n, max_w, max_d)
 plan = engine.CubePlan(grid)
 t_plan = timeit(lambda: plan.build(rows, w, mat))
 info = plan.info()
-sm_scales = engine.cube_smem_scales(n, max_w, max_d, info["mean_abs"])
-print("scales fixed", [math.log2(v) for v in scales], " smem (f64)", [math.log2(v) for v in sm_scales], " bound-only", [math.log2(v) for v in engine.cube_smem_scales(n, max_w, max_d)], flush=True)
+scales = engine.cube_fixed_scales(n, max_w, max_d, info["mean_abs"])
+print("scales fixed (capped)", [math.log2(v) for v in scales], " uncapped", [math.log2(v) for v in engine.fixed_scales(n, max_w, max_d)],
+      " smem (f64)", [math.log2(v) for v in info["smem_scales"]], flush=True)
 print("n=%d grid %dx%dx%d  plan build %.3f ms  %s  captured %.3f of the sample" % (n, nxy, nxy, nv, t_plan[0], info, info["captured"] / max(info["sampled"], 1)), flush=True)
 sums = 31 | _lib.CUBE_MOMENTS
 res = {}
@@ -36,28 +36,24 @@ for acc, sc, name in ((fx, scales, "fixed"), (f64, None, "f64")):
     ref = torch.zeros(grid.cube_moments_elems, dtype=acc.dtype, device="cuda")
     engine.project_bin(grid, rows, w, mat, 1, 1, sums, acc, sc, None, ref)
     new = torch.zeros_like(ref)
-    engine.project_cube(grid, plan, rows, w, mat, acc, sc, sm_scales, new)
+    engine.project_cube(grid, plan, rows, w, mat, acc, sc, new)
     torch.cuda.synchronize()
-    if acc is fx:
-        print("fixed: accumulators bit-identical:", bool(torch.equal(ref, new)), " mismatches:", int((ref != new).sum()), flush=True)
     # finalised maps / cube agree?
     Mr, Vr, Sr = engine.finalize_vmaps(grid, None, ref, sums, acc, sc)
     Mn, Vn, Sn = engine.finalize_vmaps(grid, None, new, sums, acc, sc)
     cr, cn = engine.finalize_cube(grid, ref, acc, sc, sums), engine.finalize_cube(grid, new, acc, sc, sums)
     rel = lambda a, b: float(((a - b).abs() / b.abs().clamp_min(1e-300)).max())
-    print("%s: max rel diff  M %.2e  cube %.2e  V(abs) %.2e  S(abs) %.2e" % (name, rel(Mn, Mr), rel(cn, cr), float((Vn - Vr).abs().max()), float((Sn - Sr).abs().max())), flush=True)
+    ok = torch.isfinite(Sr) & torch.isfinite(Sn)
+    print("%s: finalised bit-identical M %s V %s S %s cube %s | max rel diff  M %.2e  cube %.2e  V(abs) %.2e  S(abs) %.2e" % (
+        name, bool(torch.equal(Mn, Mr)), bool(torch.equal(Vn.nan_to_num(), Vr.nan_to_num())), bool(torch.equal(Sn.nan_to_num(), Sr.nan_to_num())),
+        bool(torch.equal(cn, cr)), rel(Mn, Mr), rel(cn, cr), float((Vn - Vr).nan_to_num().abs().max()), float((Sn - Sr)[ok].abs().max())), flush=True)
     buf = torch.zeros_like(ref)
     t_old = timeit(lambda: engine.project_bin(grid, rows, w, mat, 1, 1, sums, acc, sc, None, buf))
-    t_new = timeit(lambda: engine.project_cube(grid, plan, rows, w, mat, acc, sc, sm_scales, buf))
+    t_new = timeit(lambda: engine.project_cube(grid, plan, rows, w, mat, acc, sc, buf))
     print("%s: k_project_bin %.3f ms (med %.3f)   k_project_cube %.3f ms (med %.3f)   roofline frac %.3f" % (name, t_old[0], t_old[1], t_new[0], t_new[1], 28 * n / t_new[0] / 1e6 / 6448.7), flush=True)
-for shift in (-4, 4):
-    sc2 = [v / 2.0 ** shift for v in sm_scales]
-    buf = torch.zeros(grid.cube_moments_elems, dtype=torch.float64, device="cuda")
-    t = timeit(lambda: engine.project_cube(grid, plan, rows, w, mat, f64, None, sc2, buf))
-    print("f64, shared-memory scales / 2^%d: %.3f ms" % (shift, t[0]), flush=True)
 for dbg, what in ((1, "no shared-memory adds"), (2, "no in-box REDs"), (4, "no queue REDs"), (7, "loads + arithmetic only"), (3, "queue REDs only"), (5, "in-box REDs only"), (6, "shared-memory adds only")):
     os.environ["PNM_CUBE_DBG"] = str(dbg)
     buf = torch.zeros(grid.cube_moments_elems, dtype=torch.float64, device="cuda")
-    t = timeit(lambda: engine.project_cube(grid, plan, rows, w, mat, f64, None, sm_scales, buf))
+    t = timeit(lambda: engine.project_cube(grid, plan, rows, w, mat, f64, None, buf))
     print("dbg %d (%s): %.3f ms" % (dbg, what, t[0]), flush=True)
 os.environ["PNM_CUBE_DBG"] = "0"
