@@ -192,6 +192,93 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+BIG_N = 1_000_000_000
+
+
+def _sha(t):
+    import hashlib
+    return hashlib.sha256(t.detach().contiguous().cpu().numpy().tobytes()).hexdigest()[:16]
+
+
+def parity_check(pnm, engine, workloads, snap, soa, reducer, rank, world, n_local, sink):
+    """One step with int64 fixed-point accumulators through the bench's own path (k_project_cube + the reduce over
+    ranks); rank 0 then re-bins every rank's shard sequentially into ONE accumulator with the same scales and
+    compares the finalised maps and cube bit for bit."""
+    import torch
+    from pynmap_b200 import _lib
+    kw = dict(weight_name="mass", limXY=workloads.LIM_XY, nXY=NXY, limV=workloads.LIM_V, nV=NV, accumulate="fixed")
+    if reducer is not None:
+        reducer.dst = 0
+    with contextlib.redirect_stdout(sink):
+        vm, lv = snap.project(reducer=reducer, **kw)
+    torch.cuda.synchronize()
+    scales = snap.last_fixed_scales
+    if rank != 0:
+        return None
+    grid = engine.get_grid(workloads.LIM_XY, NXY, NXY, workloads.LIM_V, NV)
+    acc = engine.AccMode("fixed")
+    sums = 31 | _lib.CUBE_MOMENTS
+    _, cube = engine.new_accumulators(grid, sums, acc)
+    mat = pnm.rotation.rotation_matrix(np.float32(PA), np.float32(INCL))
+    half = (n_local // 2 + 1029) // 8 * 8
+    pieces = []
+    for r in range(world):
+        t = soa if r == 0 else workloads.make_snapshot(n_local, bulge_fraction=0.2, seed=SEED + 1000 * r, device="cuda")
+        soa_r = [t[k] for k in range(7)]
+        cuts = [(0, n_local)] if world > 1 else [(0, half), (half, n_local)]
+        for lo, hi in cuts:
+            rows = [a[lo:hi] for a in soa_r]
+            plan = engine.CubePlan(grid).build(rows[:6], rows[6], mat)
+            engine.project_cube(grid, plan, rows[:6], rows[6], mat, acc, scales, cube)
+            pieces.append(hi - lo)
+        torch.cuda.synchronize()
+        del soa_r, t
+    M, V, S = engine.finalize_vmaps(grid, None, cube, sums, acc, scales)
+    c = engine.finalize_cube(grid, cube, acc, scales, sums)
+    same = lambda a, b: bool(torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)))   # noqa: E731
+    equal = same(vm.M, M) and same(vm.V, V) and same(vm.S, S) and same(lv.losvd, c)
+    return {"checked": True, "n_ranks": world, "accumulate": "fixed", "kernel": "k_project_cube",
+            "sha256_maps": _sha(torch.stack([vm.M, vm.V, vm.S])), "sha256_cube": _sha(lv.losvd),
+            "sha256_maps_sequential": _sha(torch.stack([M, V, S])), "sha256_cube_sequential": _sha(c),
+            "equals_1rank": equal, "particles_binned": float(vm.M.sum().item()),
+            "how": ("rank 0 re-binned the %d shards one after the other into one accumulator (same scales)" % world) if world > 1
+                   else "the snapshot in one launch vs two ragged half shards (%d + %d particles) into one accumulator" % tuple(pieces)}
+
+
+def big_point(pnm, engine, workloads, n, peak, sink, accumulate):
+    """10^9 particles resident on ONE GPU: the same pipelined step, 5 timed steps after 3 warm-up steps."""
+    import torch
+    soa = workloads.make_snapshot(n, bulge_fraction=0.2, seed=SEED + 7, device="cuda")
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="torch")
+    del soa
+    snap.rotate(PA=PA, inclination=INCL)
+    post = torch.cuda.Stream(priority=-1)
+
+    def step():
+        with contextlib.redirect_stdout(sink):
+            _, lv = snap.project(weight_name="mass", limXY=workloads.LIM_XY, nXY=NXY, limV=workloads.LIM_V, nV=NV,
+                                 accumulate=accumulate, post_stream=post)
+            with torch.cuda.stream(post):
+                lv.convolve_spatial(*SMOOTH_FWHM)
+        sink.seek(0); sink.truncate()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    engine.KERNEL_TIMER = timer = engine.KernelTimer()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(5):
+        step()
+    torch.cuda.current_stream().wait_stream(post)
+    b.record(); torch.cuda.synchronize()
+    engine.KERNEL_TIMER = None
+    ms, kms = a.elapsed_time(b) / 5, timer.total_ms() / max(1, len(timer.pairs))
+    gbs = BYTES_PER_PARTICLE * n / (kms * 1e-3) / 1e9
+    return {"particles": n, "steps": 5, "ms_per_step": ms, "value": n / (ms * 1e-3), "unit": "particles/s",
+            "kernel": timer.kernel, "kernel_ms": kms, "achieved_gbs": gbs, "roofline_frac": gbs / peak}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -270,8 +357,10 @@ def run_b200(args):
     engine.KERNEL_TIMER = timer = engine.KernelTimer()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
+    enqueue_s = [time.perf_counter()]
     for _ in range(args.steps):
         step()
+    enqueue_s[0] = time.perf_counter() - enqueue_s[0]       # host time spent launching the K steps (no synchronisation inside)
     if post is not None:
         torch.cuda.current_stream().wait_stream(post)      # the last step's post-processing is inside the timed region
     t1.record()
@@ -283,31 +372,50 @@ def run_b200(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     kernel_ms = timer.total_ms() / max(1, len(timer.pairs))
+    kernel_name = timer.kernel or "k_project_bin"
+    host_enqueue_ms = enqueue_s[0] * 1e3 / args.steps
 
-    # ---- context (not part of the contract): the same step on a space-filling-curve ordered copy of the
-    # snapshot (how tree codes store particles); consecutive particles then share pixels and merge in registers
+    # ---- parity evidence: one more step with int64 fixed-point accumulators through the same
+    # kernel and the same reduce; rank 0 then bins the shards of ALL ranks one after the other into one accumulator
+    # and compares bits.  At N = 1 the comparison is the snapshot in one launch against two ragged half shards.
+    parity = None
+    if not args.no_parity:
+        parity = parity_check(pnm, engine, workloads, snap, soa, reducer, rank, world, n_local, sink)
+
+    # ---- context (not part of the contract)
     extras = None
     if rank == 0 and n_gpus == 1 and not args.no_extras:
+        extras = {}
+
+        def timed(fn, reps):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record(); torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        def plain_step(sn):
+            with contextlib.redirect_stdout(sink):
+                _, lv = sn.project(weight_name="mass", limXY=workloads.LIM_XY, nXY=NXY, limV=workloads.LIM_V, nV=NV,
+                                   accumulate=args.accumulate)
+                lv.convolve_spatial(*SMOOTH_FWHM)
+            sink.seek(0); sink.truncate()
+
+        # what a user who projects one snapshot once sees: scatter, finalise, transpose, smooth back to back on ONE stream
+        ms_np = timed(lambda: plain_step(snap), 10)
+        extras["non_pipelined_ms_per_step"] = ms_np
+        extras["non_pipelined_value"] = n_local / (ms_np * 1e-3)
+        # the same step on a space-filling-curve ordered copy of the snapshot (how tree codes store particles)
         srt = workloads.morton_sort(soa)
         snap_s = pnm.snapshot.from_arrays(srt[:3], srt[3:6], mass=srt[6], output="torch")
         snap_s.rotate(PA=PA, inclination=INCL)
-        def step_sorted():
-            with contextlib.redirect_stdout(sink):
-                _, lv = snap_s.project(weight_name="mass", limXY=workloads.LIM_XY, nXY=NXY, limV=workloads.LIM_V, nV=NV,
-                                       accumulate=args.accumulate)
-                lv.convolve_spatial(*SMOOTH_FWHM)
-            sink.seek(0); sink.truncate()
-        for _ in range(3):
-            step_sorted()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(10):
-            step_sorted()
-        b.record(); torch.cuda.synchronize()
-        ms_s = a.elapsed_time(b) / 10
-        extras = {"morton_ordered_snapshot": {"ms_per_step": ms_s, "value": n_local / (ms_s * 1e-3), "unit": "particles/s",
-                                              "note": "same step, particles pre-sorted along a 3-D Morton curve (sort not timed)"}}
+        ms_s = timed(lambda: plain_step(snap_s), 10)
+        extras["morton_ordered_snapshot"] = {"ms_per_step": ms_s, "value": n_local / (ms_s * 1e-3), "unit": "particles/s",
+                                             "note": "same step, particles pre-sorted along a 3-D Morton curve (sort not timed)"}
         del snap_s, srt
 
     # ---- end to end: pinned host buffers in, host results out, copies inside the timed region
@@ -346,17 +454,24 @@ def run_b200(args):
                "timer": "host perf_counter around synchronous calls, max over ranks"}
         del host
 
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    # ---- the north star's single-GPU size: 10^9 particles resident on one B200 (28 GB), same grid, same step
+    if extras is not None and not args.no_1e9 and n_local < BIG_N:
+        del snap, soa
+        torch.cuda.empty_cache()
+        extras["n1_1e9"] = big_point(pnm, engine, workloads, BIG_N, peak, sink, args.accumulate)
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = BYTES_PER_PARTICLE * n_local / (kernel_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("k_project_bin")
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(kernel_name)
         except Exception:
             pass
         line = {
@@ -367,22 +482,21 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": workload_name(n_gpus, n_local), "particles_per_gpu": n_local, "nXY": NXY, "nV": NV,
                        "accumulate": args.accumulate,
-                       "accumulators": "float64 (L2 reductions)" if args.accumulate == "f64" else "int64 fixed point (bit-exact, order independent)",
+                       "accumulators": ("float64; hot pixels / voxels first summed per SM in shared memory as 32-bit fixed-point limbs "
+                                        "(every term rounded by < 4.8e-7 of itself), the rest float64 reductions at L2"
+                                        if args.accumulate == "f64" else "int64 fixed point (bit-exact, order independent)"),
+                       "smoothing_parity": "unpinned (astropy absent: oracle restates convolve() from its documentation)",
                        "parallelism": "particle shards x%d + NCCL reduce of partial grids (owner rank = step %% N)" % n_gpus
                        if n_gpus > 1 else "1 GPU",
                        "l2": "inputs (2.8 GB per GPU) are 22x larger than L2, no flush needed",
                        "streams": "scatter on the main stream; fold / reduce / finalise / smooth on a post-processing "
                                   "stream (overlaps the next step's scatter)" if post is not None else "single stream"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "k_project_bin", "kernel_ms": kernel_ms,
+                         "traffic": traffic, "traffic_source": "profiles/roofline_traffic.json (ncu --set full of this kernel on "
+                         "this workload, static: not measured in this run)" if traffic else None,
+                         "kernel": kernel_name, "kernel_ms": kernel_ms, "kernel_launches_timed": len(timer.pairs),
                          "algorithmic_bytes_per_launch": BYTES_PER_PARTICLE * n_local,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         # the unit that actually bounds the scatter: L2 takes one request per
-                         # distinct 32-byte sector of a reduction instruction, ~1.87e11 scattered requests/s chip-wide
-                         # (scripts/red_pair_bench.cu, profiles/r01_micro_tma_mix.log); with the interleaved cube all
-                         # three sums of a particle share a sector: one request per particle
-                         "l2_reduction_requests": {"per_particle": 1.0, "achieved_per_s": 1.0 * n_local / (kernel_ms * 1e-3),
-                                                   "peak_per_s": 1.87e11, "frac": 1.0 * n_local / (kernel_ms * 1e-3) / 1.87e11}},
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"},
             "cpu_baseline": base,
             "e2e": e2e,
             # our kernels launched by rank 0 inside the timed region: k_project_bin every step (no replica fold: the
@@ -391,6 +505,8 @@ def run_b200(args):
             "gpu_launches": (5 * args.steps if n_gpus == 1 else
                              args.steps + 4 * len([k for k in range(args.steps) if (k + max(3, args.warmup)) % n_gpus == 0])),
             "clocks": clocks,
+            "host_enqueue_ms_per_step": host_enqueue_ms,
+            "parity": parity,
             "extras": extras,
         }
         print(json.dumps(line))
@@ -411,6 +527,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-1e9", action="store_true", help="skip the 10^9-particle single-GPU point of the extras")
     ap.add_argument("--no-pipeline", action="store_true", help="run post-processing on the scatter stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-max-ctas", type=int, default=4,

@@ -775,8 +775,7 @@ int pnm_project_cube(const pnm_grid* g, const pnm_cube_plan* pl, int64_t n, cons
 #ifdef PNM_CUBE_KNOBS
     p.dbg = env_int("PNM_CUBE_DBG", 0);
 #endif
-    cudaStream_t st = as_stream(stream);
-    PNM_CUDA(cudaMemsetAsync(pl->work, 0, sizeof(unsigned long long), st));
+    cudaStream_t st = as_stream(stream);     // (pl->work is zero: pnm_cube_plan_create, then the kernel's last CTA)
 #define PNM_LAUNCH_CUBE(ACC, HW)                                                                                    \
     do {                                                                                                            \
         auto kern = pnm::k_project_cube<ACC, HW>;                                                                   \

@@ -29,10 +29,11 @@
 // the flush adds the unsigned low limbs.
 //   * int64 accumulators (PNM_ACC_FIXED): 2^k are the caller's scales, the global path adds the very same integers
 //     -> the result is bit-identical for any plan, any CTA count, any order;
-//   * float64 accumulators: 2^k is chosen by the plan so that the sample mean of |t| lands in [2^23, 2^24): the
-//     privatised terms are rounded to 2^-24 of the typical term (the reference's float32 products already carry that
-//     much rounding each), terms up to 128 x the mean stay in shared memory, and weights below 1/16 of the typical
-//     one take the exact global path so that every voxel's sum keeps a relative accuracy better than 5e-7.
+//   * float64 accumulators: 2^k is chosen by the plan so that the sample mean of |t| lands in [2^24, 2^25): the
+//     privatised terms are rounded to 2^-25 of the typical term (the reference's float32 products already carry that
+//     much rounding each), terms up to 64 x the mean stay in shared memory, and particles with a small term (below
+//     1/16 of the typical w or w*d, see kCubeWMin) take the exact global path, so that every term is rounded by less
+//     than 4.8e-7 of itself and every pixel / voxel sum stays within 4.8e-7 * sum |term| of the float64 sum.
 // The plan only decides WHERE a sum is accumulated first, never what is summed.
 //
 // Global accumulator (PNM_CUBE_MOMENTS layout): records [G + 1][ix][iy][4], G = ceil(nv / 2);
@@ -84,8 +85,15 @@ constexpr int kCubeSmemBytes = 227 * 1024;
 constexpr int kPmStride = (kBoxPix + 32) * 4;     // bytes from the sum w*d array to the sum w*d*d array
 constexpr int kCubeSmemFixed = kBoxPix * 4 + 2 * kPmStride + kCubeWarps * kQueueCap * 16;
 constexpr int kCubeSlotsMax = (kCubeSmemBytes - kCubeSmemFixed) / 4 - 32;
-constexpr int kCubeTypBits = 23;                  // float64 mode: the sample mean of |term| * 2^k lies in [2^23, 2^24)
-constexpr float kCubeWMin = 1048576.0f;           // float64 mode: |w| * 2^k below 2^20 (1/8 .. 1/16 of the mean) -> exact global path
+#ifndef PNM_CUBE_TYP_BITS
+#define PNM_CUBE_TYP_BITS 24
+#endif
+constexpr int kCubeTypBits = PNM_CUBE_TYP_BITS;   // float64 mode: the sample mean of |term| * 2^k lies in [2^kCubeTypBits, 2 * 2^kCubeTypBits)
+// float64 mode: a particle whose scaled |w| or |w*d| is below 2^20 (1/16 .. 1/32 of the mean) or whose scaled w*d*d is
+// below 2^16 takes the exact global path with all three terms.  Every privatised term of sum w and sum w*d is
+// therefore rounded by at most 2^-21 of ITSELF (0.5 / 2^20), whatever its size: each pixel / voxel sum is within
+// 4.8e-7 * sum |term| of the unrounded float64 sum -- the 1e-6 contract, also for single-particle pixels.
+constexpr float kCubeWMin = 1048576.0f, kCubeS1Min = 1048576.0f, kCubeS2Min = 65536.0f;
 
 // table entry: base slot (16 bits) | window length (6 bits) << 16 | first velocity bin (10 bits) << 22
 constexpr int kTabBaseBits = 16, kTabLenBits = 6, kTabLenMax = (1 << kTabLenBits) - 1, kTabVloMax = 1023;
@@ -113,7 +121,7 @@ struct CubeParams {
     float sc_glob[3];                             // int64 accumulators: 2^k of (w, w*d, w*d*d), |k| <= 120 (also the shared-memory scales)
     void* cube;
     const CubePlan* plan;
-    unsigned long long* work;                     // chunk counter, zeroed by the launcher
+    unsigned long long* work;                     // work[0]: chunk counter, work[1]: finished CTAs; both zero between launches (the last CTA resets them)
     int dbg;                                      // development builds (-DPNM_CUBE_KNOBS): 1 drop the shared-memory adds, 2 the in-box REDs, 4 the queue
 };
 
@@ -297,7 +305,6 @@ __global__ void __launch_bounds__(kCubeThreads, 1) k_project_cube(const __grid_c
     const float sm0 = ACC == PNM_ACC_FIXED ? p.sc_glob[0] : plan->sc_smem[0];
     const float sm1 = ACC == PNM_ACC_FIXED ? p.sc_glob[1] : plan->sc_smem[1];
     const float sm2 = ACC == PNM_ACC_FIXED ? p.sc_glob[2] : plan->sc_smem[2];
-    const float wmin = ACC == PNM_ACC_FIXED ? 0.0f : kCubeWMin;
     const float kFit = 2147483648.0f;                  // |t * 2^k| < 2^31: rint fits 32 bits
 
     // eight queued records -> one RED instruction: lane (qj, ql) sends value ql of record qj; the three lanes of a
@@ -354,7 +361,8 @@ __global__ void __launch_bounds__(kCubeThreads, 1) k_project_cube(const __grid_c
             const unsigned bxi = (unsigned)(ix[k] - bx0), byi = (unsigned)(iy[k] - by0);
             // scaled terms; all three must fit 32 bits (NaN / inf fail), and in float64 mode w must not be tiny
             const float s0 = __fmul_rn(w, sm0), s1 = __fmul_rn(wd[k], sm1), s2 = __fmul_rn(wdd[k], sm2);
-            const bool fits = fabsf(s0) < kFit && fabsf(s1) < kFit && fabsf(s2) < kFit && fabsf(s0) >= wmin;
+            const bool big = ACC == PNM_ACC_FIXED || (fabsf(s0) >= kCubeWMin && fabsf(s1) >= kCubeS1Min && fabsf(s2) >= kCubeS2Min);
+            const bool fits = fabsf(s0) < kFit && fabsf(s1) < kFit && fabsf(s2) < kFit && big;
             in_s[k] = valid && fits && bxi < bw && byi < bh;
             queued[k] = valid && !in_s[k];
             const bool st = in_s[k] && !PNM_CUBE_DBG(1);
@@ -486,6 +494,9 @@ __global__ void __launch_bounds__(kCubeThreads, 1) k_project_cube(const __grid_c
 
     // ---- flush the shared-memory sums (unsigned low limbs): one RED per non-zero sum
     __syncthreads();
+    // every warp of this CTA has drawn its last chunk index: the last CTA to get here leaves the counters at zero
+    // for the next launch (no memset between two scatter kernels of a stream)
+    if (threadIdx.x == 0 && atomicInc(reinterpret_cast<unsigned*>(p.work + 1), gridDim.x - 1) == gridDim.x - 1) *p.work = 0ull;
     const double i0 = ACC == PNM_ACC_F64 ? plan->inv_smem[0] : 1.0, i1 = ACC == PNM_ACC_F64 ? plan->inv_smem[1] : 1.0;
     const double i2 = ACC == PNM_ACC_F64 ? plan->inv_smem[2] : 1.0;
     for (int bp = threadIdx.x; bp < nbox; bp += kCubeThreads) {

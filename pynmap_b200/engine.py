@@ -69,8 +69,18 @@ def to_device(a, dtype, device=None):
         if arr.dtype == np.bool_:
             arr = arr.astype(np.uint8)
         t = torch.from_numpy(np.ascontiguousarray(arr))
-    t = t.to(device=device, dtype=dtype, non_blocking=True)
-    return t.contiguous()
+    t = t.to(device=device, dtype=dtype, non_blocking=True).contiguous()
+    if t.data_ptr() % 32:               # a slice of a larger tensor: the vector-load kernels want aligned arrays
+        t = t.clone()
+    return t
+
+
+def alloc_soa(rows, n, dtype, device):
+    """(rows, n) device tensor whose rows start on 32-byte boundaries (row pitch rounded up to 32 bytes): the
+    vectorised scatter kernels (256-bit / 128-bit loads) want every coordinate array aligned, whatever n is."""
+    per = 32 // torch.empty(0, dtype=dtype).element_size()
+    pitch = -(-max(int(n), 1) // per) * per
+    return torch.empty((rows, pitch), dtype=dtype, device=device)[:, :n]
 
 
 def to_output(t, want_torch):
@@ -188,13 +198,17 @@ def get_grid(limXY, nx, ny, limV=None, nv=0, device=None):
 
 # ----------------------------------------------------------------------------- accumulate mode
 class AccMode(object):
-    """'f64' (default): float64 reduction atomics.  'fixed': int64 fixed point, deterministic."""
+    """'f64' (default): float64 accumulators.  'fixed': int64 fixed point, deterministic and bit-exact.
+    'f64-exact': float64 accumulators without the shared-memory privatisation of snapshot.project -- every term is
+    added with a float64 reduction at L2 (1e-12 relative vs sequential sums; 'f64' rounds the privatised terms to
+    2^-25 of the typical term and by less than 4.8e-7 of themselves: each sum within 4.8e-7 x sum|term|)."""
 
     def __init__(self, name="f64"):
-        name = {"float64": "f64", "int64": "fixed", "fixed64": "fixed"}.get(str(name), str(name))
-        if name not in ("f64", "fixed"):
-            raise ValueError("accumulate must be 'f64' or 'fixed', got %r" % (name,))
-        self.name = name
+        name = {"float64": "f64", "int64": "fixed", "fixed64": "fixed", "f64_exact": "f64-exact"}.get(str(name), str(name))
+        if name not in ("f64", "fixed", "f64-exact"):
+            raise ValueError("accumulate must be 'f64', 'f64-exact' or 'fixed', got %r" % (name,))
+        self.privatise = name != "f64-exact"
+        self.name = name = "f64" if name == "f64-exact" else name
         self.code = _lib.ACC_F64 if name == "f64" else _lib.ACC_FIXED
         self.dtype = torch.float64 if name == "f64" else torch.int64
 
@@ -223,25 +237,24 @@ def absmax(t):
 
 # ----------------------------------------------------------------------------- the scatter
 def new_accumulators(grid, sums, acc, nviews=1):
-    """Zeroed (maps, cube) accumulators.  For one view both live in ONE allocation laid out
-    [cube | map replica 0 | map replicas 1..], so that a single memset clears them and, after
-    fold_maps, the leading cube + first-replica range is all a multi-GPU reduction has to move
-    (see reduce_span)."""
+    """Zeroed (maps, cube) accumulators.  With the interleaved cube (CUBE_MOMENTS) everything lives in the cube
+    accumulator and maps is None.  Otherwise, for one view, both live in ONE allocation laid out
+    [cube | map replica 0 | map replicas 1..], so that a single memset clears them and, after fold_maps, the leading
+    cube + first-replica range is all a multi-GPU reduction has to move (see reduce_span)."""
     want_maps = bool(sums & (_lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2))
     want_cube = bool(sums & _lib.SUM_CUBE)
+    if sums & _lib.CUBE_MOMENTS:
+        return None, torch.zeros(nviews * grid.cube_moments_elems, dtype=acc.dtype, device=grid.device)
     if nviews == 1 and want_maps and want_cube:
-        moments = bool(sums & _lib.CUBE_MOMENTS)
-        ncube = grid.cube_moments_elems if moments else grid.cube_elems
-        nmaps = grid.maps_fold_elems if moments else grid.maps_elems     # one replica: the maps only take the out-of-V rest
+        ncube, nmaps = grid.cube_elems, grid.maps_elems
         pad = ncube % 2                  # keep the maps part 16-byte aligned (TMA bulk reductions)
         flat = torch.zeros(ncube + pad + nmaps, dtype=acc.dtype, device=grid.device)
         return flat[ncube + pad:], flat[:ncube]
-    moments = bool(sums & _lib.CUBE_MOMENTS)
     maps = cube = None
     if want_maps:
-        maps = torch.zeros(nviews * (grid.maps_fold_elems if moments else grid.maps_elems), dtype=acc.dtype, device=grid.device)
+        maps = torch.zeros(nviews * grid.maps_elems, dtype=acc.dtype, device=grid.device)
     if want_cube:
-        cube = torch.zeros(nviews * (grid.cube_moments_elems if moments else grid.cube_elems), dtype=acc.dtype, device=grid.device)
+        cube = torch.zeros(nviews * grid.cube_elems, dtype=acc.dtype, device=grid.device)
     return maps, cube
 
 
@@ -271,10 +284,12 @@ class KernelTimer(object):
 
     def __init__(self):
         self.pairs = []
+        self.kernel = None          # name of the kernel the last bracket timed
 
-    def bracket(self):
+    def bracket(self, kernel="k_project_bin"):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.pairs.append((a, b))
+        self.kernel = kernel
         return a, b
 
     def total_ms(self):
@@ -346,14 +361,14 @@ class CubePlan(object):
             pass
 
 
-CUBE_TYP_BITS = 23            # csrc/pnm_cube.cuh kCubeTypBits
+CUBE_TYP_BITS = 24            # csrc/pnm_cube.cuh kCubeTypBits
 
 
 def cube_fixed_scales(n_total, max_w, max_d, mean_abs):
     """int64 fixed-point scales for runs through k_project_cube: engine.fixed_scales (no overflow for n_total
-    worst-case terms), capped so that the typical term (the plan's sample mean of |term|) lands in [2^23, 2^24) --
+    worst-case terms), capped so that the typical term (the plan's sample mean of |term|) lands in [2^24, 2^25) --
     the kernel keeps a term in shared memory only when its scaled value fits 32 bits.  The cap trades resolution
-    (2^-24 of the typical term instead of ~2^-36) for speed; any power of two gives bit-exact, order-independent sums."""
+    (2^-25 of the typical term instead of ~2^-36) for speed; any power of two gives bit-exact, order-independent sums."""
     out = fixed_scales(n_total, max_w, max_d)
     for k, m in enumerate(mean_abs):
         if m > 0.0 and math.isfinite(m):
@@ -385,7 +400,7 @@ def project_cube(grid, plan, soa, w, mat, acc, scales, cube):
             ptr(soa[5]), ptr(w), m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), acc.code,
             _scales_arg(acc, scales), ptr(cube), stream_ptr())
     if KERNEL_TIMER is not None:
-        t0, t1 = KERNEL_TIMER.bracket()
+        t0, t1 = KERNEL_TIMER.bracket("k_project_cube")
         t0.record()
         try:
             _lib.call("pnm_project_cube", *args)
@@ -544,10 +559,10 @@ def fit_gh(profiles, binv, deg_gh=4, err=None, start=None, lo=None, hi=None, fix
 
 
 def rotate_soa(soa3, mat, out=None):
-    """pnm_rotate on three SoA tensors -> three new tensors (rows of a (3, N) tensor)."""
+    """pnm_rotate on three SoA tensors -> three new tensors (rows of a (3, N) tensor with aligned rows)."""
     x, y, z = soa3
     if out is None:
-        out = torch.empty((3, x.numel()), dtype=x.dtype, device=x.device)
+        out = alloc_soa(3, x.numel(), x.dtype, x.device)
     m = np.ascontiguousarray(np.asarray(mat, dtype=np.float32).reshape(9))
     _lib.call("pnm_rotate", ptr(x), ptr(y), ptr(z), ptr(out[0]), ptr(out[1]), ptr(out[2]), x.numel(),
               _TORCH_TO_PNM[x.dtype], m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), stream_ptr())

@@ -54,6 +54,12 @@ def project_host(arrays, PA, inclination, limXY, nXY, limV=None, nV=0, accumulat
     x = arrays[0]
     n = int(x.shape[0])
     code = _dtype_code(x)
+    if len(arrays) != 7 or any(a is None for a in arrays[:6]):
+        raise ValueError("host path wants (x, y, z, vx, vy, vz, w-or-None)")
+    for a in arrays:        # the C ABI only sees pointers: a shorter or differently typed array would be read out of bounds
+        if a is not None and (a.dtype != x.dtype or tuple(a.shape) != (n,)):
+            raise ValueError("host path: every array must be 1-D with %d entries of dtype %s, got shape %s dtype %s"
+                             % (n, x.dtype, tuple(a.shape), a.dtype))
     acc = engine.AccMode(accumulate)
     if acc.code == _lib.ACC_FIXED and scales is None:
         raise ValueError("fixed-point host path needs explicit scales (engine.fixed_scales)")

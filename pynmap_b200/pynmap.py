@@ -150,6 +150,8 @@ class snapshot(object):
         self.mask = (self.mass == 0)
         self._absmax = {}
         self._acc_pool = {}
+        self._cube_plans = {}
+        self._epoch = getattr(self, "_epoch", 0) + 1     # what the per-snapshot caches are keyed on (never addresses)
         self.reset()
 
     @staticmethod
@@ -158,12 +160,14 @@ class snapshot(object):
         t = a.detach() if isinstance(a, torch.Tensor) else torch.from_numpy(np.asarray(a))
         if t.dim() != 2 or 3 not in t.shape:
             raise ValueError("positions / velocities must be (N, 3) or (3, N), got %s" % (tuple(t.shape),))
-        t = t.to(device=engine.current_device(), dtype=dtype)
+        dev = engine.current_device()
         if t.shape[1] == 3 and t.shape[0] != 3:
             t = t.t()
         elif t.shape == (3, 3):
             t = t.t()   # ambiguous: follow the reference's (N, 3) convention
-        return t.contiguous()
+        out = engine.alloc_soa(3, t.shape[1], dtype, dev)      # rows on 32-byte boundaries whatever N is
+        out.copy_(t.to(device=dev))
+        return out
 
     def _check_attrs(self, list_attr=['']):
         return all(hasattr(self, attr) for attr in list_attr)
@@ -226,7 +230,8 @@ class snapshot(object):
     def reset(self):
         """Back to the original positions / velocities (pynmap/pynmap.py:238-244): drops the
         recorded matrices; no copy is made because the originals are never overwritten."""
-        self._base = self._soa
+        if getattr(self, "_base", None) is not self._soa:
+            self._new_base(self._soa)
         self._chain = []
         self._materialised = None
         self._reset_rotations()
@@ -262,8 +267,16 @@ class snapshot(object):
         return self._materialised
 
     def _rebase(self):
-        self._base = self._materialise()
+        self._new_base(self._materialise())
         self._chain = []
+
+    def _new_base(self, base):
+        """The arrays the fused kernels read have changed: everything derived from them (velocity bounds, the
+        memory-order estimate, cube plans, fixed-point scales) is forgotten."""
+        self._base = base
+        self._epoch = getattr(self, "_epoch", 0) + 1
+        self._absmax = {}
+        self._cube_plans = {}
 
     def _out(self, t):
         return t if self.output == "torch" else t.cpu().numpy()
@@ -313,30 +326,85 @@ class snapshot(object):
         return w
 
     def _max_of(self, key, tensor):
+        """max |tensor|, cached under ``key`` -- only snapshot-owned arrays have a key (the caches are cleared whenever
+        those arrays change: _ingest, _new_base); anything the caller passed in is measured on every call."""
+        if key is None:
+            return engine.absmax(tensor)
         if key not in self._absmax:
             self._absmax[key] = engine.absmax(tensor)
         return self._absmax[key]
 
-    def _fixed_scales(self, acc, w, n_total=None, reduce_max=None):
+    def _weights_key(self, w):
+        """Cache key of a weights tensor: the attribute name when it IS the snapshot's mass / flux, else None."""
+        if w is None:
+            return ("unit", 0)
+        for name in ("mass", "flux"):
+            t = getattr(self, name, None)
+            if isinstance(t, torch.Tensor) and t.data_ptr() == w.data_ptr() and t.numel() == w.numel() and t.dtype == w.dtype:
+                return (name, t._version)          # in-place torch updates of the attribute bump _version
+        return None
+
+    def _bounds(self, w):
+        """(max |w|, bound on |v_los|) for the fixed-point scales."""
+        vel = self._base[1]
+        max_v = 2.0 * max(self._max_of(("v", k), vel[k]) for k in range(3))  # |row . v| <= sqrt(3) max|v_k|
+        wkey = self._weights_key(w)
+        max_w = 1.0 if w is None else self._max_of(None if wkey is None else ("w", wkey), w)
+        return max_w, max_v
+
+    def _fixed_scales(self, acc, w, n_total=None, reduce_max=None, mean_abs=None):
         if acc.code != _lib.ACC_FIXED:
             return None
-        vel = self._base[1]
-        max_v = 2.0 * max(self._max_of(("v", id(vel), k), vel[k]) for k in range(3))  # |row . v| <= sqrt(3) max|v_k|
-        max_w = 1.0 if w is None else self._max_of(("w", w.data_ptr(), w.numel()), w)
+        max_w, max_v = self._bounds(w)
         if reduce_max is not None:            # sharded runs agree on global bounds
             max_w, max_v = reduce_max(max_w, max_v)
+        if mean_abs is not None:              # runs through k_project_cube: typical terms near 2^24 (engine.cube_fixed_scales)
+            if reduce_max is not None:
+                mean_abs = reduce_max(*mean_abs)
+            return engine.cube_fixed_scales(n_total or self.npart, max_w, max_v, mean_abs)
         return engine.fixed_scales(n_total or self.npart, max_w, max_v)
 
     def _run_fused(self, grid, w, sums, acc, scales, mats=None, nchain=None, nviews=1, mask=None, mask_mode=0,
-                   recycled=None):
+                   recycled=None, plan=None):
         pos, vel = self._base
         if mats is None:
             mats = self._chain if self._chain else [np.eye(3, dtype=np.float32)]
             nchain = len(mats)
         maps, cube = recycled if recycled is not None else engine.new_accumulators(grid, sums, acc, nviews)
         soa = (pos[0], pos[1], pos[2], vel[0], vel[1], vel[2])
-        engine.project_bin(grid, soa, w, np.stack(mats), nchain, nviews, sums, acc, scales, maps, cube, mask, mask_mode)
+        if plan is not None:
+            engine.project_cube(grid, plan, soa, w, mats[0], acc, scales, cube)
+        else:
+            engine.project_bin(grid, soa, w, np.stack(mats), nchain, nviews, sums, acc, scales, maps, cube, mask, mask_mode)
         return maps, cube
+
+    def _cube_plan(self, grid, w):
+        """The plan of the privatised scatter (engine.CubePlan) for the current view, or None when that kernel does
+        not apply (float64 particles, compounded rotations, unaligned arrays).  One plan per (grid, view), built on
+        the device from a sample of the particles; forgotten when the arrays change."""
+        if len(self._chain) > 1:
+            return None
+        pos, vel = self._base
+        soa = (pos[0], pos[1], pos[2], vel[0], vel[1], vel[2])
+        if not engine.cube_path_ok(grid, soa, w):
+            return None
+        mat = self._chain[0] if self._chain else np.eye(3, dtype=np.float32)
+        # One entry per (grid, view, weights attribute).  The plan also carries the typical term sizes that set the
+        # shared-memory / fixed-point scales, so it must follow the CONTENTS of the weights: the snapshot's own mass /
+        # flux are tracked through their torch version counter; weights the caller passes in cannot be tracked and
+        # get their plan re-built (0.4 ms, same allocation) on every call -- nothing is keyed on addresses.
+        wkey = self._weights_key(w)
+        key = (id(grid), np.asarray(mat, dtype=np.float32).tobytes(), wkey[0] if wkey else "caller")
+        entry = self._cube_plans.get(key)
+        if entry is None:
+            if len(self._cube_plans) >= 16:
+                self._cube_plans.clear()
+            plan = engine.CubePlan(grid).build(soa, w, mat)
+            entry = self._cube_plans[key] = (plan, grid, wkey)  # the grid is held so that its id stays unique
+        elif wkey is None or entry[2] != wkey:
+            entry[0].build(soa, w, mat)
+            entry = self._cube_plans[key] = (entry[0], grid, wkey)
+        return entry[0]
 
     def _mesh(self, grid):
         return grid.mesh(self.output == "torch")
@@ -478,11 +546,17 @@ class snapshot(object):
 
     # ------------------------------------------------------------------ additions (single read)
     def project(self, weights=None, weight_name=None, limXY=default_limXY, nXY=default_npoint,
-                limV=default_limV, nV=default_nVpoint, accumulate="f64", reducer=None, post_stream=None):
+                limV=default_limV, nV=default_nVpoint, accumulate="f64", reducer=None, post_stream=None,
+                privatise=None):
         """velocity_moments + create_losvds from ONE pass over the particles: returns
         (SnapMap, LOSVD) identical to calling the two methods separately.  The map's sum of
         weights is recovered from the cube (plus an out-of-range remainder), which saves one
         atomic per particle.  ``reducer(maps, cube)`` is the multi-GPU hook (sharded.py).
+
+        ``privatise``: None (default) lets float32 snapshots in no particular memory order run through the
+        shared-memory privatised kernel (csrc/pnm_cube.cuh; accumulate='f64' then rounds the privatised terms to
+        2^-25 of the typical term, accumulate='fixed' uses coarser scales -- see engine.cube_fixed_scales); False
+        forces the plain reduction kernel.
 
         ``post_stream``: a torch.cuda.Stream on which everything AFTER the scatter kernel runs
         (replica fold, the reduce over ranks, finalisation).  The scatter of the next call then
@@ -501,17 +575,30 @@ class snapshot(object):
             # Spatially ordered snapshots (tree / space-filling-curve order) keep the plain cube + replicated maps,
             # where consecutive particles of a pixel merge in registers and hot pixels are spread over replicas.
             sums |= _lib.CUBE_MOMENTS
+        want_plan = (sums & _lib.CUBE_MOMENTS) and acc.privatise and privatise is not False
+        plan = self._cube_plan(grid, w) if want_plan else None
         scales = None
         if acc.code == _lib.ACC_FIXED:
-            # sharded fixed-point runs agree on the global particle count and bounds (cached: the
-            # two tiny all-reduces end in a host read and would serialise every step)
-            key = ("fixed", id(reducer), None if w is None else w.data_ptr(), id(self._base[1]))
-            if key not in self._absmax:
+            # sharded fixed-point runs agree on the global particle count and bounds.  Cached for the snapshot's own
+            # weights only (the two tiny all-reduces end in a host read and would serialise every step); weights the
+            # caller passes in are measured again on every call -- their contents may have changed.
+            wkey = self._weights_key(w)
+            key = ("fixed", wkey, id(plan), id(reducer))
+            if wkey is None or key not in self._absmax:
                 n_total, reduce_max = (reducer.n_total(self.npart), reducer.reduce_max) if reducer else (None, None)
-                self._absmax[key] = self._fixed_scales(acc, w, n_total, reduce_max)
-            scales = self._absmax[key]
+                mean_abs = plan.info()["mean_abs"] if plan is not None else None
+                val = (self._fixed_scales(acc, w, n_total, reduce_max, mean_abs), reducer)
+                if wkey is None:
+                    scales = val[0]
+                else:
+                    self._absmax[key] = val
+            if wkey is not None:
+                scales = self._absmax[key][0]
+            if plan is not None and not engine.cube_scales_ok(scales):
+                plan = None
+        self.last_fixed_scales = scales        # (what a checker needs to reproduce the int64 sums)
         if post_stream is None:
-            maps, cube = self._run_fused(grid, w, sums, acc, scales)
+            maps, cube = self._run_fused(grid, w, sums, acc, scales, plan=plan)
             return self._project_post(grid, maps, cube, sums, acc, scales, reducer)
         # pipelined: the accumulators are recycled -- cleared on the post-processing stream once their results are
         # out, so that no memset sits between two scatter kernels on the caller's stream
@@ -521,16 +608,18 @@ class snapshot(object):
             maps, cube, cleared = pool.pop(0)
             torch.cuda.current_stream().wait_event(cleared)
             recycled = (maps, cube)
-        maps, cube = self._run_fused(grid, w, sums, acc, scales, recycled=recycled)
+        maps, cube = self._run_fused(grid, w, sums, acc, scales, recycled=recycled, plan=plan)
         scattered = torch.cuda.Event()
         scattered.record()                                   # on the caller's (scatter) stream
         post_stream.wait_event(scattered)
-        for t in (maps, cube):                               # same storage; keep it alive for the other stream
-            t.record_stream(post_stream)
+        for t in (maps, cube):                               # keep the storage alive for the other stream
+            if t is not None:
+                t.record_stream(post_stream)
         with torch.cuda.stream(post_stream):
             out = self._project_post(grid, maps, cube, sums, acc, scales, reducer)
             cube.zero_()
-            maps.zero_()
+            if maps is not None:
+                maps.zero_()
             cleared = torch.cuda.Event()
             cleared.record()
         pool.append((maps, cube, cleared))
@@ -542,7 +631,7 @@ class snapshot(object):
         runs agree on one answer (any rank ordered -> all use the plain layout): the partial grids are summed."""
         pos = self._base[0]
         pix = min((grid.limXY[1] - grid.limXY[0]) / max(grid.nx - 1, 1), (grid.limXY[3] - grid.limXY[2]) / max(grid.ny - 1, 1))
-        key = ("ordered", id(pos), float(pix), id(reducer))
+        key = ("ordered", float(pix), id(reducer))
         if key not in self._absmax:
             n = self.npart
             ordered = False

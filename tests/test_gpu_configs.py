@@ -155,7 +155,7 @@ def test_float64_particles_fused(env):
     vm, lv = snap.project(weight_name="mass", limXY=wl.LIM_XY, nXY=96, limV=wl.LIM_V, nV=64, accumulate="fixed")
     mat = on.rotation_matrix(np.float32(12.5), np.float32(77.))
     ex, ev = on.bin_edges(-15, 15, 96), on.bin_edges(-500, 500, 64)
-    scales = snap._fixed_scales(engine.AccMode("fixed"), snap.mass)
+    scales = snap.last_fixed_scales
     fmaps, fcube = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, ex, ex, ev, 31, oc.ACC_FIXED, scales)
     Mf, Vf, Sf = oc.finalize_vmaps(fmaps[0], fcube[0], 31, oc.ACC_FIXED, scales)
     assert same(vm.M, Mf) and same(vm.V, Vf) and same(vm.S, Sf)
@@ -209,7 +209,7 @@ def test_host_path_single_and_sharded_flavours(env):
     pinned.copy_(soa)
     snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="numpy")
     snap.rotate(PA=30., inclination=60.)
-    vm, lv = snap.project(weight_name="mass", limXY=wl.LIM_XY, nXY=64, limV=wl.LIM_V, nV=32)
+    vm, lv = snap.project(weight_name="mass", limXY=wl.LIM_XY, nXY=64, limV=wl.LIM_V, nV=32, accumulate="f64-exact")   # every term a float64 reduction, like the host path
     sm = lv.convolve_spatial(1.0, 1.0)
     single = hostpath.project_host([host[k] for k in range(7)], 30., 60., wl.LIM_XY, 64, wl.LIM_V, 32, smooth_fwhm=(1.0, 1.0))
     calls = []
@@ -218,7 +218,7 @@ def test_host_path_single_and_sharded_flavours(env):
         return True
     sharded = hostpath.project_host([pinned[k] for k in range(7)], 30., 60., wl.LIM_XY, 64, wl.LIM_V, 32,
                                     smooth_fwhm=(1.0, 1.0), reducer=fake_reducer)
-    assert calls == [[64 * 64 * 16 * 4 + 64 * 64 * 4]]   # one contiguous span: interleaved cube (nV/2 records of 4) + folded maps
+    assert calls == [[64 * 64 * (16 + 1) * 4]]              # one span: the interleaved cube (nV/2 + 1 record slabs of 4)
     for res in (single, sharded):
         assert close(res["M"], vm.M) and rel_err(res["V"], vm.V, floor=1e-3) < 1e-9
         assert np.allclose(res["cube"], sm.losvd, rtol=1e-10, atol=1e-12 * sm.losvd.max())
@@ -256,7 +256,7 @@ def test_sharded_project_with_post_stream_matches_plain(env):
     hook.reduce_max = lambda *v: v
     vm1, lv1 = whole.project(reducer=hook, post_stream=post, **kw)
     post.synchronize()
-    assert seen == [96 * 96 * 32 * 4 + 96 * 96 * 4]       # one contiguous span: interleaved cube + the folded map replica
+    assert seen == [96 * 96 * (32 + 1) * 4]               # one span: the interleaved cube (nV/2 + 1 record slabs)
     for a, b in ((vm0.M, vm1.M), (vm0.V, vm1.V), (vm0.S, vm1.S), (lv0.losvd, lv1.losvd)):
         assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
 
@@ -268,7 +268,9 @@ def test_sharded_project_with_post_stream_matches_plain(env):
         parts["a"] = [t.clone() for t in tensors]
         return False
     hook_a.n_total = lambda n_local: n
-    hook_a.reduce_max = lambda *v: (max(v[0], bounds[0]), max(v[1], bounds[1])) if len(v) == 2 else v   # scales | layout vote
+    # what the ranks would agree on: global bounds (2 values), typical term sizes (3 values), the layout vote (1 value)
+    hook_a.reduce_max = lambda *v: ((max(v[0], bounds[0]), max(v[1], bounds[1])) if len(v) == 2 else
+                                    (1.0, 128.0, 16384.0) if len(v) == 3 else v)
 
     def hook_b(*tensors):
         for t, other in zip(tensors, parts["a"]):
@@ -303,7 +305,7 @@ def test_ordered_snapshot_uses_plain_layout_same_results(env):
         s.rotate(PA=30., inclination=60.)
         grid = engine.get_grid(workloads.LIM_XY, 64, 64, workloads.LIM_V, 48)
         assert s._memory_ordered(grid) is want_ordered
-        out.append(s.project(**kw))
+        out.append(s.project(privatise=False, **kw))      # (the privatised kernel would pick coarser fixed-point scales)
     (vm_a, lv_a), (vm_b, lv_b) = out
     for a, b in ((vm_a.M, vm_b.M), (vm_a.V, vm_b.V), (vm_a.S, vm_b.S), (lv_a.losvd, lv_b.losvd)):
         assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
@@ -326,7 +328,7 @@ def test_interleaved_cube_odd_and_tiny_velocity_axes(env):
         grid = engine.get_grid(lim, 40, 24, limv, nv)
         assert not snap._memory_ordered(grid)
         vm, lv = snap.project(weight_name="mass", limXY=lim, nXY=[40, 24], limV=limv, nV=nv, accumulate="fixed")
-        scales = snap._fixed_scales(engine.AccMode("fixed"), snap.mass)
+        scales = snap.last_fixed_scales
         ex, ey, ev = on.bin_edges(lim[0], lim[1], 40), on.bin_edges(lim[2], lim[3], 24), on.bin_edges(limv[0], limv[1], nv)
         omaps, ocube = oc.project_bin(list(host[:6]), host[6], mat, 1, 1, ex, ey, ev, 15 | 16, oc.ACC_FIXED, scales)
         Mo, Vo, So = oc.finalize_vmaps(omaps[0], ocube[0], 15 | 16, oc.ACC_FIXED, scales)
@@ -353,10 +355,10 @@ def test_interleaved_cube_two_views_in_one_launch(env):
     for k, mat in enumerate(mats):
         maps1, cube1 = engine.new_accumulators(grid, sums, fx)
         engine.project_bin(grid, rows, soa[6], mat, 1, 1, sums, fx, scales, maps1, cube1)
-        nm, nc = grid.maps_fold_elems, grid.cube_moments_elems
-        assert torch.equal(maps2[k * nm:(k + 1) * nm], maps1) and torch.equal(cube2[k * nc:(k + 1) * nc], cube1)
-        got = engine.finalize_vmaps(grid, maps2[k * nm:(k + 1) * nm], cube2[k * nc:(k + 1) * nc], sums, fx, scales)
-        want = engine.finalize_vmaps(grid, maps1, cube1, sums, fx, scales)
+        nc = grid.cube_moments_elems
+        assert maps1 is None and maps2 is None and torch.equal(cube2[k * nc:(k + 1) * nc], cube1)   # everything lives in the cube records
+        got = engine.finalize_vmaps(grid, None, cube2[k * nc:(k + 1) * nc], sums, fx, scales)
+        want = engine.finalize_vmaps(grid, None, cube1, sums, fx, scales)
         assert all(torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0)) for a, b in zip(got, want))
 
 
