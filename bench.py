@@ -207,15 +207,19 @@ def parity_check(pnm, engine, workloads, snap, soa, reducer, rank, world, n_loca
     import torch
     from pynmap_b200 import _lib
     kw = dict(weight_name="mass", limXY=workloads.LIM_XY, nXY=NXY, limV=workloads.LIM_V, nV=NV, accumulate="fixed")
+    grid = engine.get_grid(workloads.LIM_XY, NXY, NXY, workloads.LIM_V, NV)
     if reducer is not None:
         reducer.dst = 0
     with contextlib.redirect_stdout(sink):
         vm, lv = snap.project(reducer=reducer, **kw)
+    if getattr(reducer, "scatter_slabs", False):         # every rank holds its own velocity bins: assemble them on rank 0
+        whole = reducer.gather_losvd(lv.losvd, grid, dst=0)
+        if rank == 0:
+            lv.losvd = whole
     torch.cuda.synchronize()
     scales = snap.last_fixed_scales
     if rank != 0:
         return None
-    grid = engine.get_grid(workloads.LIM_XY, NXY, NXY, workloads.LIM_V, NV)
     acc = engine.AccMode("fixed")
     sums = 31 | _lib.CUBE_MOMENTS
     _, cube = engine.new_accumulators(grid, sums, acc)
@@ -307,13 +311,18 @@ def run_b200(args):
     import pynmap_b200 as pnm
     import workloads
     from pynmap_b200 import engine, hostpath
-    from pynmap_b200.sharded import GridReducer
+    from pynmap_b200.sharded import GridReducer, SlabReducer
 
     pnm._lib.require_device()
     soa = workloads.make_snapshot(n_local, bulge_fraction=0.2, seed=SEED + 1000 * rank, device="cuda")
     snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="torch")
     snap.rotate(PA=PA, inclination=INCL)
-    reducer = GridReducer() if world > 1 else None
+    reducer = e2e_reducer = None
+    if world > 1:
+        # the scatter kernel is persistent (one CTA per SM): what runs next to it needs SMs of its own
+        reserve = args.reserve_sms if args.reserve_sms >= 0 else 0
+        reducer = GridReducer(reserve_sms=reserve) if args.reduce == "owner" else SlabReducer(reserve_sms=reserve)
+        e2e_reducer = GridReducer()
     sink = io.StringIO()
 
     # post-processing stream: replica fold, NCCL reduce, finalisation and smoothing of step k run
@@ -323,7 +332,7 @@ def run_b200(args):
     counter = [0]
 
     def step():
-        if reducer is not None:
+        if reducer is not None and args.reduce == "owner":
             # round-robin owner: step k's grids are reduced to, finalised and smoothed on rank k % N,
             # so that the post-processing load is spread over the ranks instead of piling up on rank 0
             reducer.dst = counter[0] % world
@@ -346,7 +355,7 @@ def run_b200(args):
 
     # setup, not warm-up: NCCL builds its connections lazily per reduce root, so every owner rank is
     # used once before the W warm-up steps (otherwise a short W leaves connection setup in the timed region)
-    for _ in range(world if reducer is not None else 0):
+    for _ in range(world if reducer is not None and args.reduce == "owner" else 0):
         step()
     fence()
     for _ in range(max(3, args.warmup)):
@@ -432,7 +441,7 @@ def run_b200(args):
 
         def e2e_step():
             return hostpath.project_host(rows, PA, INCL, workloads.LIM_XY, NXY, workloads.LIM_V, NV,
-                                         accumulate="f64", smooth_fwhm=SMOOTH_FWHM, reducer=reducer, out=out)
+                                         accumulate="f64", smooth_fwhm=SMOOTH_FWHM, reducer=e2e_reducer, out=out)
 
         e2e_steps = max(1, min(args.steps, args.e2e_steps))
         for _ in range(2):
@@ -486,8 +495,12 @@ def run_b200(args):
                                         "(every term rounded by < 4.8e-7 of itself), the rest float64 reductions at L2"
                                         if args.accumulate == "f64" else "int64 fixed point (bit-exact, order independent)"),
                        "smoothing_parity": "unpinned (astropy absent: oracle restates convolve() from its documentation)",
-                       "parallelism": "particle shards x%d + NCCL reduce of partial grids (owner rank = step %% N)" % n_gpus
-                       if n_gpus > 1 else "1 GPU",
+                       "parallelism": ("1 GPU" if n_gpus == 1 else
+                                       "particle shards x%d + NCCL reduce of partial grids (owner rank = step %% N)" % n_gpus
+                                       if args.reduce == "owner" else
+                                       "particle shards x%d + NCCL reduce-scatter of the partial grids along the velocity axis "
+                                       "(every rank finalises and smooths its own nV/N velocity bins; the smoothed cube stays "
+                                       "sharded) + all-reduce of the per-pixel map sums (maps on every rank)" % n_gpus),
                        "l2": "inputs (2.8 GB per GPU) are 22x larger than L2, no flush needed",
                        "streams": "scatter on the main stream; fold / reduce / finalise / smooth on a post-processing "
                                   "stream (overlaps the next step's scatter)" if post is not None else "single stream"},
@@ -503,7 +516,9 @@ def run_b200(args):
             # interleaved cube has a single map replica); k_finalize_vmaps, k_cube_out, k_smooth_axis<0>, <1> on the
             # steps it owns
             "gpu_launches": (5 * args.steps if n_gpus == 1 else
-                             args.steps + 4 * len([k for k in range(args.steps) if (k + max(3, args.warmup)) % n_gpus == 0])),
+                             args.steps + 4 * len([k for k in range(args.steps) if (k + max(3, args.warmup)) % n_gpus == 0])
+                             if args.reduce == "owner" else
+                             6 * args.steps),      # k_project_cube, k_slab_sums, k_finalize_sums, k_cube_out_slabs, k_smooth_axis<0>, <1>
             "clocks": clocks,
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "parity": parity,
@@ -533,6 +548,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nccl-max-ctas", type=int, default=4,
                     help="cap on the CTAs of the NCCL reduce, which shares the SMs with the scatter kernel (0 = NCCL's choice)")
+    ap.add_argument("--reserve-sms", type=int, default=0,
+                    help="SMs the persistent scatter kernel leaves idle for the collective at N > 1")
+    ap.add_argument("--reduce", default="scatter", choices=["scatter", "owner"],
+                    help="N > 1: reduce-scatter along the velocity axis (every rank post-processes its own bins) or reduce to a rotating owner")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -265,6 +265,19 @@ int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t
                double guess_h, double empty_m2, double ftol, double xtol, double gtol, int32_t maxiter,
                double* gh, double* bestfit, int32_t* status, int32_t* niter, double* chi2, void* stream);
 
+/* ---- slab-sharded finalisation (multi-GPU; new: the reference is a single process) ----------
+ * The PNM_CUBE_MOMENTS accumulator is an array of record slabs [g][ix][iy][4], g <= G = ceil(nv / 2).  After a
+ * reduce-scatter over ranks along g, a rank holds slabs [g0, g1) of the total (`slabs` points at slab g0; slabs past
+ * G are padding).  pnm_slab_sums: that rank's share of (sum w, sum w*d, sum w*d*d) per pixel, accumulator type,
+ * [3][nx*ny] in (ix, iy) order -- summed over ranks by an all-reduce (exact for int64); pnm_finalize_sums: the totals
+ * -> M, V, S (grid.py:133-138, (nY, nX) float64 like pnm_finalize_vmaps); pnm_finalize_cube_slabs: the rank's
+ * velocity bins [2 g0, min(nv, 2 g1)) of the LOSVD cube as float64 (nX, nY, bins) (grid.py:259).                 */
+int pnm_slab_sums(const pnm_grid* g, const void* slabs, int32_t g0, int32_t g1, int acc_mode, void* sums3, void* stream);
+int pnm_finalize_sums(const pnm_grid* g, const void* sums3, int acc_mode, const double* scales3_host,
+                      double* M, double* V, double* S, void* stream);
+int pnm_finalize_cube_slabs(const pnm_grid* g, const void* slabs, int32_t g0, int32_t g1, int acc_mode, double scale_w,
+                            double* cube_out, void* stream);
+
 /* ---- max |a[i]| over n elements -> out_dev[0] (float64, device); used to pick FIXED scales -- */
 int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream);
 
@@ -277,10 +290,11 @@ int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* strea
  * grid changes -- a stale plan only costs speed, never correctness).
  *   PNM_ACC_FIXED: bit-identical to pnm_project_bin with the same scales for any plan.  scales3_host must be powers
  *                  of two in [2^-120, 2^120]; a term stays in shared memory only while |term * 2^k| < 2^31, so scales
- *                  that put the typical term near 2^23 (pnm_cube_plan_info reports such scales) are the fast ones.
- *   PNM_ACC_F64  : privatised terms are rounded to 2^-24 of the sample mean of |term| (weights below 1/16 of the
- *                  typical one, terms above 128 x the typical one and non-finite terms take the exact RED path):
- *                  per-voxel / per-pixel sums agree with pnm_project_bin to better than 5e-7 relative.
+ *                  that put the typical term near 2^24 (pnm_cube_plan_info reports such scales) are the fast ones.
+ *   PNM_ACC_F64  : privatised terms are rounded to 2^-25 of the sample mean of |term|; particles with a term below
+ *                  ~1/16 of the typical w or w*d, above 64 x the typical one or non-finite take the exact RED path,
+ *                  so every term is rounded by less than 4.8e-7 of itself: each per-voxel / per-pixel sum agrees
+ *                  with pnm_project_bin to better than 4.8e-7 x sum |term|.
  * Particle arrays must be 16-byte aligned; n < 2^32.  Launches that share a plan must be ordered on one stream (the
  * plan owns the kernel's work counter).
  *   pnm_cube_plan_info (synchronises `stream`): out8_host = { box x0, y0, width, height, voxel slots used, threshold
@@ -294,6 +308,9 @@ int pnm_cube_plan_build(const pnm_grid* g, pnm_cube_plan* plan, int64_t n, const
                         const float* vx, const float* vy, const float* vz, const float* w, const float* mat9_host,
                         void* stream);
 int pnm_cube_plan_info(const pnm_cube_plan* plan, int32_t* out8_host, double* stats6_host, void* stream);
+/* SMs pnm_project_cube leaves idle (0 .. 64; default 0): the kernel is persistent with one CTA per SM, so a collective
+ * or post-processing kernel of another stream can only run next to it on SMs it does not take (sharded runs).      */
+int pnm_cube_plan_set_reserved_sms(pnm_cube_plan* plan, int32_t nsm);
 int pnm_project_cube(const pnm_grid* g, const pnm_cube_plan* plan, int64_t n, const float* x, const float* y,
                      const float* z, const float* vx, const float* vy, const float* vz, const float* w,
                      const float* mat9_host, int acc_mode, const double* scales3_host, void* acc_cube, void* stream);

@@ -63,11 +63,15 @@ _SIGNATURES = {
                                  POINTER(c_double), c_int, POINTER(c_double),
                                  POINTER(c_double), c_int32, POINTER(c_double), c_int32, _P, _P, _P, _P]),
     "pnm_host_release": (c_int, []),
+    "pnm_slab_sums": (c_int, [_P, _P, c_int32, c_int32, c_int, _P, _P]),
+    "pnm_finalize_sums": (c_int, [_P, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),
+    "pnm_finalize_cube_slabs": (c_int, [_P, _P, c_int32, c_int32, c_int, c_double, _P, _P]),
     "pnm_cube_slots_max": (c_int32, []),
     "pnm_cube_plan_create": (c_int, [_P, POINTER(_P)]),
     "pnm_cube_plan_destroy": (c_int, [_P]),
     "pnm_cube_plan_build": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, POINTER(c_float), _P]),
     "pnm_cube_plan_info": (c_int, [_P, POINTER(c_int32), POINTER(c_double), _P]),
+    "pnm_cube_plan_set_reserved_sms": (c_int, [_P, c_int32]),
     "pnm_project_cube": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P, POINTER(c_float), c_int,
                                  POINTER(c_double), _P, _P]),
 }

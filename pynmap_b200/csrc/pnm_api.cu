@@ -398,6 +398,65 @@ int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int sums, int acc
     return PNM_OK;
 }
 
+// ------------------------------------------------------------------------------------ slab-sharded finalisation
+namespace {
+int slab_args(const char* who, const pnm_grid* g, const void* slabs, int g0, int g1, int acc_mode) {
+    if (!g || !slabs) return fail(PNM_EINVAL, "%s: null argument", who);
+    if (g->nv < 1) return fail(PNM_EINVAL, "%s: the grid has no V axis", who);
+    if (g0 < 0 || g1 < g0) return fail(PNM_EINVAL, "%s: slab range [%d, %d)", who, g0, g1);
+    if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "%s: acc_mode %d", who, acc_mode);
+    return PNM_OK;
+}
+}  // namespace
+
+int pnm_slab_sums(const pnm_grid* g, const void* slabs, int32_t g0, int32_t g1, int acc_mode, void* sums3, void* stream) {
+    const int rc = slab_args("pnm_slab_sums", g, slabs, g0, g1, acc_mode);
+    if (rc != PNM_OK) return rc;
+    if (!sums3) return fail(PNM_EINVAL, "pnm_slab_sums: sums3 is null");
+    const int npix = g->nx * g->ny, G = (g->nv + 1) / 2;
+    const int grid = (npix + 255) / 256;
+    if (acc_mode == PNM_ACC_F64) pnm::k_slab_sums<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(slabs, npix, g0, g1, G, sums3);
+    else pnm::k_slab_sums<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(slabs, npix, g0, g1, G, sums3);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_finalize_sums(const pnm_grid* g, const void* sums3, int acc_mode, const double* scales3_host, double* M, double* V,
+                      double* S, void* stream) {
+    if (!g || !sums3) return fail(PNM_EINVAL, "pnm_finalize_sums: null argument");
+    const int npix = g->nx * g->ny;
+    const int grid = (npix + 255) / 256;
+    if (acc_mode == PNM_ACC_F64) {
+        pnm::k_finalize_sums<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(sums3, g->nx, g->ny, 1.0, 1.0, 1.0, M, V, S);
+    } else if (acc_mode == PNM_ACC_FIXED) {
+        if (!scales3_host) return fail(PNM_EINVAL, "pnm_finalize_sums: FIXED mode needs scales");
+        pnm::k_finalize_sums<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(sums3, g->nx, g->ny, 1.0 / scales3_host[0],
+                                                                              1.0 / scales3_host[1], 1.0 / scales3_host[2], M, V, S);
+    } else {
+        return fail(PNM_EINVAL, "pnm_finalize_sums: acc_mode %d", acc_mode);
+    }
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
+int pnm_finalize_cube_slabs(const pnm_grid* g, const void* slabs, int32_t g0, int32_t g1, int acc_mode, double scale_w,
+                            double* cube_out, void* stream) {
+    const int rc = slab_args("pnm_finalize_cube_slabs", g, slabs, g0, g1, acc_mode);
+    if (rc != PNM_OK) return rc;
+    const int iv0 = std::min(2 * g0, g->nv), iv1 = std::min(2 * g1, g->nv);
+    const int nvl = iv1 - iv0;
+    if (nvl <= 0) return PNM_OK;                     // this rank holds no velocity bins (only padding / the rest slab)
+    if (!cube_out) return fail(PNM_EINVAL, "pnm_finalize_cube_slabs: cube_out is null");
+    const int npix = g->nx * g->ny;
+    const dim3 grid((npix + 31) / 32, (nvl + 31) / 32), block(32, 8);
+    if (acc_mode == PNM_ACC_F64)
+        pnm::k_cube_out_slabs<PNM_ACC_F64><<<grid, block, 0, as_stream(stream)>>>(slabs, cube_out, npix, g0, iv0, nvl, 1.0);
+    else
+        pnm::k_cube_out_slabs<PNM_ACC_FIXED><<<grid, block, 0, as_stream(stream)>>>(slabs, cube_out, npix, g0, iv0, nvl, 1.0 / scale_w);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
 int pnm_fold_maps(const pnm_grid* g, void* acc_maps, int acc_mode, int clear_others, void* stream) {
     if (!g || !acc_maps) return fail(PNM_EINVAL, "pnm_fold_maps: null argument");
     if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_fold_maps: acc_mode %d", acc_mode);
@@ -627,6 +686,7 @@ struct pnm_cube_plan {
     pnm::CubePlan* plan;
     pnm::PlanScratch s;
     unsigned long long* work;       // chunk counter of k_project_cube
+    int reserved_sms;               // SMs k_project_cube leaves to other streams
     bool built;
 };
 
@@ -673,7 +733,7 @@ int pnm_cube_plan_create(const pnm_grid* g, pnm_cube_plan** out) {
     *out = nullptr;
     if (!g || g->nv < 1) return fail(PNM_EINVAL, "pnm_cube_plan_create: needs a grid with a V axis");
     pnm_cube_plan* pl = new pnm_cube_plan();
-    pl->nx = g->nx; pl->ny = g->ny; pl->nv = g->nv; pl->built = false;
+    pl->nx = g->nx; pl->ny = g->ny; pl->nv = g->nv; pl->built = false; pl->reserved_sms = 0;
     auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
     const size_t b_col = up(sizeof(uint32_t) * g->nx), b_row = up(sizeof(uint32_t) * g->ny), b_tot = up(sizeof(uint32_t) * pnm::kPlanLevels);
     const size_t b_sum = up(sizeof(double) * 4);
@@ -701,6 +761,12 @@ int pnm_cube_plan_create(const pnm_grid* g, pnm_cube_plan** out) {
     pl->plan = reinterpret_cast<pnm::CubePlan*>(b); b += b_plan;
     pl->work = reinterpret_cast<unsigned long long*>(b);
     *out = pl;
+    return PNM_OK;
+}
+
+int pnm_cube_plan_set_reserved_sms(pnm_cube_plan* pl, int32_t nsm) {
+    if (!pl || nsm < 0 || nsm > 64) return fail(PNM_EINVAL, "pnm_cube_plan_set_reserved_sms: plan is null or nsm outside 0..64");
+    pl->reserved_sms = nsm;
     return PNM_OK;
 }
 
@@ -771,7 +837,7 @@ int pnm_project_cube(const pnm_grid* g, const pnm_cube_plan* pl, int64_t n, cons
     }
     p.cube = acc_cube; p.plan = pl->plan; p.work = pl->work;
     const int64_t nchunks = (n + pnm::kCubeChunk - 1) / pnm::kCubeChunk;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(pnm::kNumSMs, (nchunks + pnm::kCubeWarps - 1) / pnm::kCubeWarps));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(pnm::kNumSMs - pl->reserved_sms, (nchunks + pnm::kCubeWarps - 1) / pnm::kCubeWarps));
 #ifdef PNM_CUBE_KNOBS
     p.dbg = env_int("PNM_CUBE_DBG", 0);
 #endif

@@ -207,6 +207,73 @@ __global__ void __launch_bounds__(256) k_cube_out(const void* acc_cube, double* 
     }
 }
 
+// ---------------------------------------------------------------- slab-sharded finalisation (multi-GPU)
+// After a reduce-scatter over ranks along the record-slab axis of the interleaved cube (records [g][q][4]), a rank
+// holds the slabs g0 <= g < g1 of the TOTAL.  k_slab_sums gives that rank's share of the three map sums per pixel
+// (q order, accumulator type: the shares are summed over ranks by an all-reduce, exactly for int64), k_finalize_sums
+// turns the totals into M, V, S (grid.py:133-138, same roundings as k_finalize_vmaps), k_cube_out_slabs writes the
+// rank's velocity bins [iv0, iv0 + nvl) of the LOSVD cube as float64 [q][nvl] (grid.py:259).
+template <int ACC>
+__global__ void __launch_bounds__(256) k_slab_sums(const void* slabs, int npix, int g0, int g1, int G, void* sums3) {
+    using A = typename AccT<ACC>::type;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npix) return;
+    const A* c = reinterpret_cast<const A*>(slabs);
+    A t0 = 0, t1 = 0, t2 = 0;
+    for (int g = g0; g < g1 && g <= G; ++g) {
+        const A* rec = c + ((int64_t)(g - g0) * npix + q) * 4;
+        t0 += rec[0] + rec[1]; t1 += rec[2]; t2 += rec[3];
+    }
+    A* o = reinterpret_cast<A*>(sums3);
+    o[q] = t0; o[npix + q] = t1; o[2 * npix + q] = t2;
+}
+
+template <int ACC>
+__global__ void __launch_bounds__(256) k_finalize_sums(const void* sums3, int nx, int ny, double is0, double is1, double is2,
+                                                       double* M, double* V, double* S) {
+    using A = typename AccT<ACC>::type;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;     // = ix*ny + iy
+    const int npix = nx * ny;
+    if (q >= npix) return;
+    const A* a = reinterpret_cast<const A*>(sums3);
+    const double s0 = (ACC == PNM_ACC_F64) ? (double)a[q] : __dmul_rn((double)a[q], is0);
+    const double s1 = (ACC == PNM_ACC_F64) ? (double)a[npix + q] : __dmul_rn((double)a[npix + q], is1);
+    const double s2 = (ACC == PNM_ACC_F64) ? (double)a[2 * npix + q] : __dmul_rn((double)a[2 * npix + q], is2);
+    double v = 0.0, sg = 0.0;
+    if (s0 != 0.0) {
+        v = __ddiv_rn(s1, s0);
+        sg = __dsqrt_rn(__dsub_rn(__ddiv_rn(s2, s0), __dmul_rn(v, v)));
+    }
+    const int ix = q / ny, iy = q - ix * ny;
+    const int pix = iy * nx + ix;                            // map layout [iy][ix] (the reference's .T)
+    if (M) M[pix] = s0;
+    if (V) V[pix] = v;
+    if (S) S[pix] = sg;
+}
+
+template <int ACC>
+__global__ void __launch_bounds__(256) k_cube_out_slabs(const void* slabs, double* out, int npix, int g0, int iv0, int nvl,
+                                                        double inv_scale) {
+    __shared__ double tile[32][33];
+    const int q0 = blockIdx.x * 32, v0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int il = v0 + r, q = q0 + threadIdx.x;          // il: velocity bin relative to iv0
+        double val = 0.0;
+        if (il < nvl && q < npix) {
+            const int iv = iv0 + il;
+            const int64_t at = ((int64_t)((iv >> 1) - g0) * npix + q) * 4 + (iv & 1);
+            val = (ACC == PNM_ACC_F64) ? reinterpret_cast<const double*>(slabs)[at]
+                                       : __dmul_rn((double)reinterpret_cast<const long long*>(slabs)[at], inv_scale);
+        }
+        tile[r][threadIdx.x] = val;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int q = q0 + r, il = v0 + threadIdx.x;
+        if (q < npix && il < nvl) out[(int64_t)q * nvl + il] = tile[threadIdx.x][r];
+    }
+}
+
 // ---------------------------------------------------------------- K4: separable Gaussian
 // cube [nx][ny][nv], iv contiguous.  One pass convolves along AXIS (0 or 1) with zero fill:
 //   out[i] = sum_t taps[t] * in[i + (t - r) * stride_axis]

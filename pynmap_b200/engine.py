@@ -148,6 +148,15 @@ class Grid(object):
         plus one record slab for the particles outside the V range."""
         return self.nx * self.ny * ((self.nv + 1) // 2 + 1) * 4
 
+    @property
+    def record_slabs(self):
+        """Record slabs of the interleaved cube: G = ceil(nv / 2) velocity-bin pairs + the out-of-range slab."""
+        return (self.nv + 1) // 2 + 1
+
+    @property
+    def slab_elems(self):
+        return self.nx * self.ny * 4
+
     def centres(self):
         """Pixel centres (grid.py:141-142, :247-249); fresh arrays, the caller may keep them."""
         px = np.linspace(self.limXY[0], self.limXY[1], self.nx)
@@ -236,14 +245,18 @@ def absmax(t):
 
 
 # ----------------------------------------------------------------------------- the scatter
-def new_accumulators(grid, sums, acc, nviews=1):
-    """Zeroed (maps, cube) accumulators.  With the interleaved cube (CUBE_MOMENTS) everything lives in the cube
+def new_accumulators(grid, sums, acc, nviews=1, slab_multiple=1):
+    """Zeroed (maps, cube) accumulators.  ``slab_multiple``: the interleaved cube is padded with empty record slabs
+    to a multiple of that many slabs (a reduce-scatter over ranks wants equal chunks).  With the interleaved cube (CUBE_MOMENTS) everything lives in the cube
     accumulator and maps is None.  Otherwise, for one view, both live in ONE allocation laid out
     [cube | map replica 0 | map replicas 1..], so that a single memset clears them and, after fold_maps, the leading
     cube + first-replica range is all a multi-GPU reduction has to move (see reduce_span)."""
     want_maps = bool(sums & (_lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2))
     want_cube = bool(sums & _lib.SUM_CUBE)
     if sums & _lib.CUBE_MOMENTS:
+        if slab_multiple > 1 and nviews == 1:
+            nslab = -(-grid.record_slabs // slab_multiple) * slab_multiple
+            return None, torch.zeros(nslab * grid.slab_elems, dtype=acc.dtype, device=grid.device)
         return None, torch.zeros(nviews * grid.cube_moments_elems, dtype=acc.dtype, device=grid.device)
     if nviews == 1 and want_maps and want_cube:
         ncube, nmaps = grid.cube_elems, grid.maps_elems
@@ -340,6 +353,13 @@ class CubePlan(object):
                   ptr(soa[0]), ptr(soa[1]), ptr(soa[2]), ptr(soa[3]), ptr(soa[4]), ptr(soa[5]), ptr(w),
                   m.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), stream_ptr())
         self._info = None
+        return self
+
+    def reserve_sms(self, nsm):
+        """Leave ``nsm`` SMs idle in project_cube launches with this plan (room for a collective of another stream)."""
+        if nsm != getattr(self, "_reserved", 0):
+            _lib.call("pnm_cube_plan_set_reserved_sms", self.handle, int(nsm))
+            self._reserved = int(nsm)
         return self
 
     def info(self):
@@ -446,6 +466,39 @@ def finalize_cube(grid, cube, acc, scales, sums=0):
     return out
 
 
+def slab_sums(grid, slabs, g0, g1, acc):
+    """pnm_slab_sums: this rank's share of (sum w, sum w*d, sum w*d*d) per pixel from the record slabs [g0, g1) it
+    holds (``slabs`` starts at slab g0) -> (3, nx*ny) tensor of the accumulator type."""
+    out = torch.empty((3, grid.nx * grid.ny), dtype=acc.dtype, device=grid.device)
+    _lib.call("pnm_slab_sums", grid.handle, ptr(slabs), int(g0), int(g1), acc.code, ptr(out), stream_ptr())
+    return out
+
+
+def finalize_sums(grid, sums3, acc, scales):
+    """pnm_finalize_sums: total (sum w, sum w*d, sum w*d*d) per pixel -> M, V, S as float64 (nY, nX) tensors."""
+    shape = (grid.ny, grid.nx)
+    M, V, S = (torch.empty(shape, dtype=torch.float64, device=grid.device) for _ in range(3))
+    _lib.call("pnm_finalize_sums", grid.handle, ptr(sums3), acc.code, _scales_arg(acc, scales), ptr(M), ptr(V), ptr(S),
+              stream_ptr())
+    return M, V, S
+
+
+def slab_vrange(grid, g0, g1):
+    """Velocity bins [iv0, iv1) carried by the record slabs [g0, g1)."""
+    return min(2 * g0, grid.nv), min(2 * g1, grid.nv)
+
+
+def finalize_cube_slabs(grid, slabs, g0, g1, acc, scales):
+    """pnm_finalize_cube_slabs: the velocity bins of the record slabs [g0, g1) -> float64 (nX, nY, bins) tensor
+    (possibly with zero bins: a rank that only holds padding or the out-of-range slab)."""
+    iv0, iv1 = slab_vrange(grid, g0, g1)
+    out = torch.empty((grid.nx, grid.ny, iv1 - iv0), dtype=torch.float64, device=grid.device)
+    scale = float(scales[0]) if acc.code == _lib.ACC_FIXED else 1.0
+    if iv1 > iv0:
+        _lib.call("pnm_finalize_cube_slabs", grid.handle, ptr(slabs), int(g0), int(g1), acc.code, scale, ptr(out), stream_ptr())
+    return out
+
+
 def fold_maps(grid, maps, acc, clear=True):
     """Sum the map replicas into the first one; returns the view that carries the totals (what a
     multi-GPU reduction has to move).  ``clear=False`` leaves the other replicas untouched: cheaper,
@@ -477,6 +530,8 @@ def smooth_cube(cube, taps_axis0, taps_axis1):
     cube = cube.contiguous()
     nx, ny, nv = cube.shape
     out = torch.empty_like(cube)
+    if cube.numel() == 0:                # (a rank of a slab-sharded run may hold no velocity bins)
+        return out
     work = torch.empty_like(cube)
     t0, t1 = _lib.doubles(taps_axis0), _lib.doubles(taps_axis1)
     _lib.call("pnm_smooth_cube", ptr(cube), ptr(out), ptr(work), nx, ny, nv, t0, len(taps_axis0), t1,

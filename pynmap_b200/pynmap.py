@@ -365,12 +365,12 @@ class snapshot(object):
         return engine.fixed_scales(n_total or self.npart, max_w, max_v)
 
     def _run_fused(self, grid, w, sums, acc, scales, mats=None, nchain=None, nviews=1, mask=None, mask_mode=0,
-                   recycled=None, plan=None):
+                   recycled=None, plan=None, slab_multiple=1):
         pos, vel = self._base
         if mats is None:
             mats = self._chain if self._chain else [np.eye(3, dtype=np.float32)]
             nchain = len(mats)
-        maps, cube = recycled if recycled is not None else engine.new_accumulators(grid, sums, acc, nviews)
+        maps, cube = recycled if recycled is not None else engine.new_accumulators(grid, sums, acc, nviews, slab_multiple)
         soa = (pos[0], pos[1], pos[2], vel[0], vel[1], vel[2])
         if plan is not None:
             engine.project_cube(grid, plan, soa, w, mats[0], acc, scales, cube)
@@ -570,13 +570,17 @@ class snapshot(object):
         grid = engine.get_grid(limXY, n2[0], n2[1], limV, int(nV))
         w = self._weights_on_device(weights)
         sums = _lib.SUM_W | _lib.SUM_WD | _lib.SUM_WD2 | _lib.SUM_CUBE | _lib.W_FROM_CUBE
-        if not self._memory_ordered(grid, reducer):
+        slabs = bool(getattr(reducer, "scatter_slabs", False))      # sharded.SlabReducer: reduce-scatter along the record slabs
+        slab_multiple = reducer.world if slabs else 1
+        if slabs or not self._memory_ordered(grid, reducer):
             # particles in no particular order: all three sums of a particle into ONE sector of the interleaved cube.
             # Spatially ordered snapshots (tree / space-filling-curve order) keep the plain cube + replicated maps,
             # where consecutive particles of a pixel merge in registers and hot pixels are spread over replicas.
             sums |= _lib.CUBE_MOMENTS
         want_plan = (sums & _lib.CUBE_MOMENTS) and acc.privatise and privatise is not False
         plan = self._cube_plan(grid, w) if want_plan else None
+        if plan is not None:      # sharded runs: the collective of the previous step runs next to this scatter
+            plan.reserve_sms(getattr(reducer, "reserve_sms", 0) if post_stream is not None else 0)
         scales = None
         if acc.code == _lib.ACC_FIXED:
             # sharded fixed-point runs agree on the global particle count and bounds.  Cached for the snapshot's own
@@ -598,17 +602,17 @@ class snapshot(object):
                 plan = None
         self.last_fixed_scales = scales        # (what a checker needs to reproduce the int64 sums)
         if post_stream is None:
-            maps, cube = self._run_fused(grid, w, sums, acc, scales, plan=plan)
+            maps, cube = self._run_fused(grid, w, sums, acc, scales, plan=plan, slab_multiple=slab_multiple)
             return self._project_post(grid, maps, cube, sums, acc, scales, reducer)
         # pipelined: the accumulators are recycled -- cleared on the post-processing stream once their results are
         # out, so that no memset sits between two scatter kernels on the caller's stream
-        pool = self._acc_pool.setdefault((id(grid), sums, acc.code), [])
+        pool = self._acc_pool.setdefault((id(grid), sums, acc.code, slab_multiple), [])
         recycled = None
         if len(pool) >= 2:                                   # the older of two sets: its clearing finished a step ago
             maps, cube, cleared = pool.pop(0)
             torch.cuda.current_stream().wait_event(cleared)
             recycled = (maps, cube)
-        maps, cube = self._run_fused(grid, w, sums, acc, scales, recycled=recycled, plan=plan)
+        maps, cube = self._run_fused(grid, w, sums, acc, scales, recycled=recycled, plan=plan, slab_multiple=slab_multiple)
         scattered = torch.cuda.Event()
         scattered.record()                                   # on the caller's (scatter) stream
         post_stream.wait_event(scattered)
@@ -646,6 +650,8 @@ class snapshot(object):
 
     def _project_post(self, grid, maps, cube, sums, acc, scales, reducer):
         """Everything after the scatter of project(): fold + reduce over ranks, finalisation."""
+        if getattr(reducer, "scatter_slabs", False):
+            return self._project_post_slabs(grid, cube, acc, scales, reducer)
         if reducer is not None:
             if not sums & _lib.CUBE_MOMENTS:                   # (the interleaved layout has a single map replica)
                 engine.fold_maps(grid, maps, acc, clear=False) # single-use accumulators: nothing adds to them again
@@ -660,6 +666,24 @@ class snapshot(object):
         px, py, pv = grid.centres()
         mylosvd = LOSVD(px, py, pv, self._out(engine.finalize_cube(grid, cube, acc, scales, sums)))
         mylosvd.PAs, mylosvd.inclinations = self.PAs, self.inclinations
+        return newmap, mylosvd
+
+    def _project_post_slabs(self, grid, cube, acc, scales, reducer):
+        """Sharded post-processing (sharded.SlabReducer): reduce-scatter of the record slabs, every rank finalises
+        its own velocity bins; the maps come from an all-reduce of the per-rank partial sums (3 values per pixel).
+        -> (SnapMap, LOSVD of this rank's velocity bins) on every rank."""
+        g0, g1 = reducer.slab_range(grid)
+        mine = reducer.scatter(cube, grid)
+        sums3 = reducer.all_sum(engine.slab_sums(grid, mine, g0, g1, acc))
+        M, V, S = (self._out(t) for t in engine.finalize_sums(grid, sums3, acc, scales))
+        X, Y = self._mesh(grid)
+        newmap = SnapMap(name="Velocity moments", input_dic={"X": X, "Y": Y, "V": V, "M": M, "S": S,
+                                                              "PAs": self.PAs, "inclinations": self.inclinations})
+        px, py, pv = grid.centres()
+        iv0, iv1 = engine.slab_vrange(grid, g0, g1)
+        mylosvd = LOSVD(px, py, pv[iv0:iv1], self._out(engine.finalize_cube_slabs(grid, mine, g0, g1, acc, scales)))
+        mylosvd.PAs, mylosvd.inclinations = self.PAs, self.inclinations
+        mylosvd.vrange = (iv0, iv1)                            # which velocity bins of the whole cube these are
         return newmap, mylosvd
 
     def project_views(self, PAs, inclinations, weights=None, weight_name=None, limXY=default_limXY,

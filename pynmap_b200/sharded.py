@@ -28,10 +28,11 @@ class GridReducer(object):
 
     all_ranks=False: reduce to ``dst`` (only that rank finalises); True: all-reduce."""
 
-    def __init__(self, group=None, dst=0, all_ranks=False):
+    def __init__(self, group=None, dst=0, all_ranks=False, reserve_sms=0):
         if not dist.is_initialized():
             raise RuntimeError("GridReducer needs an initialised torch.distributed process group")
         self.group, self.dst, self.all_ranks = group, dst, all_ranks
+        self.reserve_sms = int(reserve_sms)      # SMs the persistent scatter kernel leaves to the collective (pipelined runs)
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
 
@@ -59,3 +60,53 @@ class GridReducer(object):
             else:
                 dist.reduce(t, dst=self.dst, op=dist.ReduceOp.SUM, group=self.group)
         return self.all_ranks or self.rank == self.dst
+
+
+class SlabReducer(GridReducer):
+    """Reduce-scatter flavour for ``snapshot.project``: the interleaved cube accumulator is an array of record slabs
+    (pairs of velocity bins x all pixels), padded to a multiple of the world size; a reduce-scatter leaves every rank
+    with the TOTAL of its own contiguous slab range.  Each rank then finalises and smooths its own velocity bins
+    (smoothing acts per velocity slice), and the moment maps come from a small all-reduce of per-rank partial sums
+    (3 values per pixel).  Compared with a reduce to one owner the post-processing is spread evenly over the ranks
+    and nothing has to rotate.  ``project`` returns, on every rank, the full SnapMap and the LOSVD of the rank's
+    velocity bins (``gather_losvd`` assembles the whole cube where it is wanted)."""
+
+    scatter_slabs = True
+
+    def chunk_slabs(self, grid):
+        """Record slabs per rank."""
+        return -(-grid.record_slabs // self.world)
+
+    def slab_range(self, grid, rank=None):
+        c = self.chunk_slabs(grid)
+        r = self.rank if rank is None else rank
+        return r * c, (r + 1) * c
+
+    def scatter(self, acc_padded, grid):
+        """acc_padded: world * chunk_slabs record slabs (this rank's partial sums) -> this rank's slabs of the total."""
+        per = self.chunk_slabs(grid) * grid.slab_elems
+        if acc_padded.numel() != per * self.world:
+            raise ValueError("accumulator of %d elements, expected %d (padded to the world size)" % (acc_padded.numel(), per * self.world))
+        if dist.get_backend(self.group) == "gloo":          # gloo has no reduce-scatter: sum everything, keep the own chunk
+            dist.all_reduce(acc_padded, op=dist.ReduceOp.SUM, group=self.group)
+            return acc_padded[self.rank * per:(self.rank + 1) * per]
+        out = torch.empty(per, dtype=acc_padded.dtype, device=acc_padded.device)
+        dist.reduce_scatter_tensor(out, acc_padded, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
+    def all_sum(self, t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def gather_losvd(self, local_cube, grid, dst=None):
+        """(nX, nY, own bins) float64 cubes of all ranks -> the whole (nX, nY, nV) cube on rank ``dst`` (None: on every
+        rank); other ranks get None."""
+        c = self.chunk_slabs(grid)
+        pad = torch.zeros((grid.nx, grid.ny, 2 * c), dtype=local_cube.dtype, device=local_cube.device)
+        pad[:, :, :local_cube.shape[2]] = local_cube
+        parts = torch.empty(self.world * pad.numel(), dtype=pad.dtype, device=pad.device)
+        dist.all_gather_into_tensor(parts, pad.reshape(-1), group=self.group)
+        if dst is not None and dst != self.rank:
+            return None
+        parts = parts.reshape((self.world,) + tuple(pad.shape))
+        return parts.permute(1, 2, 0, 3).reshape(grid.nx, grid.ny, self.world * 2 * c)[:, :, :grid.nv].contiguous()

@@ -274,3 +274,74 @@ def test_bench_path_full_size_against_oracle(env):
     Mq, Vq, Sq = oc.finalize_vmaps(omaps[0], ocube[0], 15 | 16)
     assert same(vm_q.M.cpu().numpy(), Mq) and same(lv_q.losvd.cpu().numpy(), ocube[0])
     assert moments_within_contract(vm_q.V.cpu().numpy(), vm_q.S.cpu().numpy(), Vq, Sq)
+
+
+def test_slab_finalisation_equals_whole_accumulator(env):
+    """pnm_slab_sums / pnm_finalize_sums / pnm_finalize_cube_slabs on the chunks a reduce-scatter over 1, 2, 3 and 8
+    ranks would leave == pnm_finalize_vmaps / pnm_finalize_cube on the whole interleaved accumulator: bit for bit with
+    int64 accumulators (odd and even velocity axes; ranks that only hold padding), to rounding with float64."""
+    pnm, wl = env
+    from pynmap_b200 import engine, _lib
+    n = 600_000
+    soa = wl.make_snapshot(n, seed=81, device="cuda", unit_mass=False)
+    rows = [soa[k] for k in range(6)]
+    mat = on.rotation_matrix(np.float32(30.), np.float32(60.))
+    sums = 31 | _lib.CUBE_MOMENTS
+    for nv in (33, 8, 1):
+        grid = engine.get_grid(wl.LIM_XY, 40, 24, wl.LIM_V, nv)
+        for mode in ("fixed", "f64"):
+            acc = engine.AccMode(mode)
+            scales = engine.fixed_scales(n, engine.absmax(soa[6]), 2.0 * max(engine.absmax(r) for r in rows[3:])) if mode == "fixed" else None
+            for world in (1, 2, 3, 8):
+                _, cube = engine.new_accumulators(grid, sums, acc, slab_multiple=world)
+                c = -(-grid.record_slabs // world)
+                assert cube.numel() == c * world * grid.slab_elems
+                engine.project_bin(grid, rows, soa[6], mat, 1, 1, sums, acc, scales, None, cube)
+                Mw, Vw, Sw = engine.finalize_vmaps(grid, None, cube, sums, acc, scales)
+                cw = engine.finalize_cube(grid, cube, acc, scales, sums)
+                per = c * grid.slab_elems
+                total, parts = None, []
+                for r in range(world):
+                    chunk = cube[r * per:(r + 1) * per]
+                    share = engine.slab_sums(grid, chunk, r * c, (r + 1) * c, acc)
+                    total = share if total is None else total + share
+                    parts.append(engine.finalize_cube_slabs(grid, chunk, r * c, (r + 1) * c, acc, scales))
+                    assert parts[-1].shape[2] == max(0, min(nv, 2 * (r + 1) * c) - min(nv, 2 * r * c))
+                M, V, S = engine.finalize_sums(grid, total, acc, scales)
+                assert torch.equal(torch.cat(parts, dim=2), cw)
+                if mode == "fixed":
+                    assert tsame(M, Mw) and tsame(V, Vw) and tsame(S, Sw)
+                else:
+                    assert torch.allclose(M, Mw, rtol=1e-13, atol=0) and torch.allclose(V, Vw, rtol=1e-9, atol=1e-9, equal_nan=True)
+
+
+def test_project_through_slab_reducer_single_rank(env):
+    """snapshot.project(reducer=SlabReducer-like) with one rank: the reduce-scatter path (padded accumulator, slab sums,
+    finalisation of the own velocity bins, smoothing) returns the plain project() bits, also pipelined on a side stream."""
+    pnm, wl = env
+    n = 700_001
+    soa = wl.make_snapshot(n, seed=82, device="cuda", unit_mass=False)
+
+    class OneRank(object):                                    # sharded.SlabReducer without a process group
+        scatter_slabs, world, rank, reserve_sms = True, 1, 0, 0
+        def chunk_slabs(self, grid): return grid.record_slabs
+        def slab_range(self, grid, rank=None): return 0, grid.record_slabs
+        def scatter(self, acc, grid): return acc
+        def all_sum(self, t): return t
+        def n_total(self, n_local): return n_local
+        def reduce_max(self, *v): return v
+
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="torch")
+    snap.rotate(PA=30., inclination=60.)
+    kw = dict(weight_name="mass", limXY=wl.LIM_XY, nXY=[48, 40], limV=wl.LIM_V, nV=37, accumulate="fixed")
+    vm0, lv0 = snap.project(**kw)
+    sm0 = lv0.convolve_spatial(1.0, 1.0)
+    post = torch.cuda.Stream()
+    for stream in (None, post, post, post):
+        vm1, lv1 = snap.project(reducer=OneRank(), post_stream=stream, **kw)
+        with (torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())):
+            sm1 = lv1.convolve_spatial(1.0, 1.0)
+        torch.cuda.synchronize()
+        assert lv1.vrange == (0, 37)
+        assert tsame(vm1.M, vm0.M) and tsame(vm1.V, vm0.V) and tsame(vm1.S, vm0.S)
+        assert torch.equal(lv1.losvd, lv0.losvd) and torch.equal(sm1.losvd, sm0.losvd)

@@ -75,3 +75,74 @@ def test_two_rank_reduce_is_bit_identical_to_one_rank(tmp_path):
     assert int(z["n_total"]) == n
     maps, cube = oc.project_bin(soa, w, mat, 1, 1, ex, ex, ev, 15, oc.ACC_FIXED, z["scales"])
     assert np.array_equal(maps, z["maps"]) and np.array_equal(cube, z["cube"])
+
+
+# ---------------------------------------------------------------------------------------------- slab reducer
+class _FakeGrid(object):
+    """The attributes sharded.SlabReducer reads from engine.Grid (no device needed)."""
+    def __init__(self, nx, ny, nv):
+        self.nx, self.ny, self.nv = nx, ny, nv
+        self.record_slabs = (nv + 1) // 2 + 1
+        self.slab_elems = nx * ny * 4
+
+
+def _interleave(maps_rest, s1, s2, cube, nslab_pad):
+    """numpy restatement of the PNM_CUBE_MOMENTS layout (include/pnm_b200.h): records [g][q][4] =
+    { w of bin 2g, w of bin 2g+1, sum w*d, sum w*d*d }; the moments and the out-of-range weights sit in slab G."""
+    nv, npix = cube.shape
+    G = (nv + 1) // 2
+    acc = np.zeros((nslab_pad, npix, 4), dtype=cube.dtype)
+    for iv in range(nv):
+        acc[iv // 2, :, iv & 1] = cube[iv]
+    acc[G, :, 0], acc[G, :, 2], acc[G, :, 3] = maps_rest, s1, s2
+    return acc
+
+
+def _slab_worker(rank, world, port, nv, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pynmap_b200.sharded import SlabReducer
+    nx, ny = 6, 5
+    npix = nx * ny
+    grid = _FakeGrid(nx, ny, nv)
+    red = SlabReducer()
+    c = red.chunk_slabs(grid)
+    assert c * world >= grid.record_slabs and red.slab_range(grid) == (rank * c, (rank + 1) * c)
+    rng = np.random.default_rng(100 + rank)
+    cube = rng.integers(0, 1000, (nv, npix)).astype(np.int64)
+    rest, s1, s2 = (rng.integers(-500, 500, npix).astype(np.int64) for _ in range(3))
+    mine = _interleave(rest, s1, s2, cube, c * world)
+    total = torch.from_numpy(mine.copy())
+    dist.all_reduce(total)                                   # what the ranks together hold
+    chunk = red.scatter(torch.from_numpy(mine.reshape(-1).copy()), grid)
+    g0, g1 = red.slab_range(grid)
+    assert torch.equal(chunk.reshape(c, npix, 4), total[g0:g1])
+    # per-rank share of the map sums, all-reduced == the sums over every slab of the total
+    part = chunk.reshape(c, npix, 4)
+    share = torch.stack([part[:, :, 0].sum(0) + part[:, :, 1].sum(0), part[:, :, 2].sum(0), part[:, :, 3].sum(0)])
+    sums3 = red.all_sum(share.clone())
+    want = torch.stack([total[:, :, 0].sum(0) + total[:, :, 1].sum(0), total[:, :, 2].sum(0), total[:, :, 3].sum(0)])
+    assert torch.equal(sums3, want)
+    # own velocity bins -> the whole cube on rank 0 only / on every rank
+    iv0, iv1 = min(2 * g0, nv), min(2 * g1, nv)
+    local = torch.empty((nx, ny, iv1 - iv0), dtype=torch.float64)
+    for iv in range(iv0, iv1):
+        local[:, :, iv - iv0] = part[iv // 2 - g0, :, iv & 1].reshape(nx, ny).double()
+    whole = red.gather_losvd(local, grid, dst=0)
+    everywhere = red.gather_losvd(local, grid)
+    ref = torch.stack([total[iv // 2, :, iv & 1].reshape(nx, ny).double() for iv in range(nv)], dim=2)
+    assert (whole is None) == (rank != 0) and torch.equal(everywhere, ref)
+    if rank == 0:
+        assert torch.equal(whole, ref)
+        np.savez(out_path, ok=np.array(1))
+    dist.destroy_process_group()
+
+
+def test_slab_reducer_two_and_three_ranks(tmp_path):
+    """sharded.SlabReducer on gloo: chunking of the padded record slabs, reduce-scatter (all-reduce + slice on gloo),
+    the all-reduced map sums and the gather of the per-rank velocity bins -- odd and even velocity axes, more ranks than
+    some chunk boundaries like."""
+    for world, nv in ((2, 8), (3, 7), (2, 1)):
+        out = str(tmp_path / ("slab_%d_%d.npz" % (world, nv)))
+        mp.spawn(_slab_worker, args=(world, _free_port(), nv, out), nprocs=world, join=True)
+        assert os.path.isfile(out)
