@@ -311,7 +311,7 @@ def run_b200(args):
     import pynmap_b200 as pnm
     import workloads
     from pynmap_b200 import engine, hostpath
-    from pynmap_b200.sharded import GridReducer, SlabReducer
+    from pynmap_b200.sharded import GridReducer, PeerSlabReducer, SlabReducer
 
     pnm._lib.require_device()
     soa = workloads.make_snapshot(n_local, bulge_fraction=0.2, seed=SEED + 1000 * rank, device="cuda")
@@ -321,7 +321,8 @@ def run_b200(args):
     if world > 1:
         # the scatter kernel is persistent (one CTA per SM): what runs next to it needs SMs of its own
         reserve = args.reserve_sms if args.reserve_sms >= 0 else 0
-        reducer = GridReducer(reserve_sms=reserve) if args.reduce == "owner" else SlabReducer(reserve_sms=reserve)
+        reducer = (GridReducer(reserve_sms=reserve) if args.reduce == "owner" else
+                   SlabReducer(reserve_sms=reserve) if args.reduce == "scatter" else PeerSlabReducer())
         e2e_reducer = GridReducer()
     sink = io.StringIO()
 
@@ -330,8 +331,35 @@ def run_b200(args):
     post = None if args.no_pipeline else torch.cuda.Stream(priority=-1)
 
     counter = [0]
+    deferred = world > 1 and args.reduce == "peer"
+    if deferred:
+        post = None                              # software pipelining on ONE stream instead (see step())
+    pending = [None]
+
+    def finish(p):
+        with contextlib.redirect_stdout(sink):
+            vmap, losvd = p.result()
+            losvd = losvd.convolve_spatial(*SMOOTH_FWHM)
+        sink.seek(0)
+        sink.truncate()
+        return vmap, losvd
+
+    def drain():
+        if pending[0] is not None:
+            finish(pending[0])
+            pending[0] = None
 
     def step():
+        if deferred:
+            # scatter of step k, then the finalisation of step k - 1 whose chunks were pulled from the peers by the copy
+            # engines while the scatter kernels ran: all on one stream, nothing competes with the persistent kernel for SMs
+            with contextlib.redirect_stdout(sink):
+                cur = snap.project(weight_name="mass", limXY=workloads.LIM_XY, nXY=NXY, limV=workloads.LIM_V, nV=NV,
+                                   accumulate=args.accumulate, reducer=reducer, deferred=True)
+            if pending[0] is not None:
+                finish(pending[0])
+            pending[0] = cur
+            return None, None
         if reducer is not None and args.reduce == "owner":
             # round-robin owner: step k's grids are reduced to, finalised and smoothed on rank k % N,
             # so that the post-processing load is spread over the ranks instead of piling up on rank 0
@@ -348,6 +376,7 @@ def run_b200(args):
         return vmap, losvd
 
     def fence():
+        drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -369,6 +398,7 @@ def run_b200(args):
     enqueue_s = [time.perf_counter()]
     for _ in range(args.steps):
         step()
+    drain()                                                 # (deferred mode: the last step's finalisation is inside the timed region)
     enqueue_s[0] = time.perf_counter() - enqueue_s[0]       # host time spent launching the K steps (no synchronisation inside)
     if post is not None:
         torch.cuda.current_stream().wait_stream(post)      # the last step's post-processing is inside the timed region
@@ -498,12 +528,20 @@ def run_b200(args):
                        "parallelism": ("1 GPU" if n_gpus == 1 else
                                        "particle shards x%d + NCCL reduce of partial grids (owner rank = step %% N)" % n_gpus
                                        if args.reduce == "owner" else
+                                       "particle shards x%d; the partial grids live in symmetric memory and every rank pulls its "
+                                       "nV/N velocity bins of all ranks' grids over NVLink with the copy engines while the next "
+                                       "scatter kernel runs (deferred finalisation), sums them in rank order, finalises and smooths "
+                                       "them (the smoothed cube stays sharded along V) + all-reduce of the per-pixel map sums "
+                                       "(maps on every rank)" % n_gpus
+                                       if args.reduce == "peer" else
                                        "particle shards x%d + NCCL reduce-scatter of the partial grids along the velocity axis "
                                        "(every rank finalises and smooths its own nV/N velocity bins; the smoothed cube stays "
                                        "sharded) + all-reduce of the per-pixel map sums (maps on every rank)" % n_gpus),
                        "l2": "inputs (2.8 GB per GPU) are 22x larger than L2, no flush needed",
-                       "streams": "scatter on the main stream; fold / reduce / finalise / smooth on a post-processing "
-                                  "stream (overlaps the next step's scatter)" if post is not None else "single stream"},
+                       "streams": ("scatter on the main stream; fold / reduce / finalise / smooth on a post-processing "
+                                   "stream (overlaps the next step's scatter)" if post is not None else
+                                   "one compute stream (scatter k, then finalisation of step k-1) + a copy stream for the "
+                                   "peer-to-peer pulls" if deferred else "single stream")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": "profiles/roofline_traffic.json (ncu --set full of this kernel on "
                          "this workload, static: not measured in this run)" if traffic else None,
@@ -518,7 +556,7 @@ def run_b200(args):
             "gpu_launches": (5 * args.steps if n_gpus == 1 else
                              args.steps + 4 * len([k for k in range(args.steps) if (k + max(3, args.warmup)) % n_gpus == 0])
                              if args.reduce == "owner" else
-                             6 * args.steps),      # k_project_cube, k_slab_sums, k_finalize_sums, k_cube_out_slabs, k_smooth_axis<0>, <1>
+                             (7 if args.reduce == "peer" else 6) * args.steps),   # k_project_cube, (k_sum_chunks,) k_slab_sums, k_finalize_sums, k_cube_out_slabs, k_smooth_axis<0>, <1>
             "clocks": clocks,
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "parity": parity,
@@ -550,8 +588,9 @@ def main():
                     help="cap on the CTAs of the NCCL reduce, which shares the SMs with the scatter kernel (0 = NCCL's choice)")
     ap.add_argument("--reserve-sms", type=int, default=0,
                     help="SMs the persistent scatter kernel leaves idle for the collective at N > 1")
-    ap.add_argument("--reduce", default="scatter", choices=["scatter", "owner"],
-                    help="N > 1: reduce-scatter along the velocity axis (every rank post-processes its own bins) or reduce to a rotating owner")
+    ap.add_argument("--reduce", default="peer", choices=["peer", "scatter", "owner"],
+                    help="N > 1: peer = copy-engine pulls over NVLink from symmetric memory + local sum (every rank post-processes "
+                         "its own velocity bins); scatter = the same with an NCCL reduce-scatter; owner = NCCL reduce to a rotating owner")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

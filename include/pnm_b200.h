@@ -272,6 +272,13 @@ int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t
  * [3][nx*ny] in (ix, iy) order -- summed over ranks by an all-reduce (exact for int64); pnm_finalize_sums: the totals
  * -> M, V, S (grid.py:133-138, (nY, nX) float64 like pnm_finalize_vmaps); pnm_finalize_cube_slabs: the rank's
  * velocity bins [2 g0, min(nv, 2 g1)) of the LOSVD cube as float64 (nX, nY, bins) (grid.py:259).                 */
+/* out[i] = sum over r < nchunks of chunks[r * per + i], added in index order (8-byte accumulator elements, 16-byte
+ * aligned arrays): the local reduction of a peer-to-peer reduce-scatter -- every rank pulls its chunk of every
+ * rank's partial grid into `chunks` with the copy engines and sums them here, in rank order.                       */
+/* cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, stream): device pointers of this or of a peer device (unified
+ * addressing) -- the copy-engine pull of the peer-to-peer reduce-scatter.                                          */
+int pnm_copy_async(void* dst, const void* src, int64_t nbytes, void* stream);
+int pnm_sum_chunks(const void* chunks, int32_t nchunks, int64_t per, int acc_mode, void* out, void* stream);
 int pnm_slab_sums(const pnm_grid* g, const void* slabs, int32_t g0, int32_t g1, int acc_mode, void* sums3, void* stream);
 int pnm_finalize_sums(const pnm_grid* g, const void* sums3, int acc_mode, const double* scales3_host,
                       double* M, double* V, double* S, void* stream);

@@ -409,6 +409,25 @@ int slab_args(const char* who, const pnm_grid* g, const void* slabs, int g0, int
 }
 }  // namespace
 
+int pnm_copy_async(void* dst, const void* src, int64_t nbytes, void* stream) {
+    if (nbytes < 0 || (nbytes > 0 && (!dst || !src))) return fail(PNM_EINVAL, "pnm_copy_async: bad argument");
+    if (nbytes == 0) return PNM_OK;
+    PNM_CUDA(cudaMemcpyAsync(dst, src, (size_t)nbytes, cudaMemcpyDefault, as_stream(stream)));
+    return PNM_OK;
+}
+
+int pnm_sum_chunks(const void* chunks, int32_t nchunks, int64_t per, int acc_mode, void* out, void* stream) {
+    if (!chunks || !out || nchunks < 1 || per < 0) return fail(PNM_EINVAL, "pnm_sum_chunks: bad argument");
+    if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_sum_chunks: acc_mode %d", acc_mode);
+    if ((reinterpret_cast<uintptr_t>(chunks) | reinterpret_cast<uintptr_t>(out)) & 15) return fail(PNM_EINVAL, "pnm_sum_chunks: arrays must be 16-byte aligned");
+    if (per == 0) return PNM_OK;
+    const int grid = grid_for((per + 1) / 2, 256, 8);
+    if (acc_mode == PNM_ACC_F64) pnm::k_sum_chunks<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(chunks, nchunks, per, out);
+    else pnm::k_sum_chunks<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(chunks, nchunks, per, out);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
 int pnm_slab_sums(const pnm_grid* g, const void* slabs, int32_t g0, int32_t g1, int acc_mode, void* sums3, void* stream) {
     const int rc = slab_args("pnm_slab_sums", g, slabs, g0, g1, acc_mode);
     if (rc != PNM_OK) return rc;

@@ -213,6 +213,33 @@ __global__ void __launch_bounds__(256) k_cube_out(const void* acc_cube, double* 
 // (q order, accumulator type: the shares are summed over ranks by an all-reduce, exactly for int64), k_finalize_sums
 // turns the totals into M, V, S (grid.py:133-138, same roundings as k_finalize_vmaps), k_cube_out_slabs writes the
 // rank's velocity bins [iv0, iv0 + nvl) of the LOSVD cube as float64 [q][nvl] (grid.py:259).
+// out[i] = chunks[0][i] + chunks[1][i] + ... in index order (the same order on every rank: deterministic float64 sums);
+// `chunks` = nchunks arrays of `per` elements back to back.  128-bit loads, grid-stride.
+template <int ACC>
+__global__ void __launch_bounds__(256) k_sum_chunks(const void* chunks, int nchunks, int64_t per, void* out) {
+    using A = typename AccT<ACC>::type;
+    const A* c = reinterpret_cast<const A*>(chunks);
+    A* o = reinterpret_cast<A*>(out);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 2;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < per; i += stride) {
+        if (i + 1 < per && (per & 1) == 0) {
+            A a0 = 0, a1 = 0;
+            for (int r = 0; r < nchunks; ++r) {
+                const longlong2 v = *reinterpret_cast<const longlong2*>(c + (int64_t)r * per + i);
+                if (ACC == PNM_ACC_F64) { a0 = (A)__dadd_rn((double)a0, __longlong_as_double(v.x)); a1 = (A)__dadd_rn((double)a1, __longlong_as_double(v.y)); }
+                else { a0 += (A)v.x; a1 += (A)v.y; }
+            }
+            o[i] = a0; o[i + 1] = a1;
+        } else {
+            for (int64_t j = i; j < per && j < i + 2; ++j) {
+                A a = 0;
+                for (int r = 0; r < nchunks; ++r) a += c[(int64_t)r * per + j];
+                o[j] = a;
+            }
+        }
+    }
+}
+
 template <int ACC>
 __global__ void __launch_bounds__(256) k_slab_sums(const void* slabs, int npix, int g0, int g1, int G, void* sums3) {
     using A = typename AccT<ACC>::type;

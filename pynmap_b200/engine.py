@@ -34,7 +34,9 @@ def current_device():
 
 
 def stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current CUDA stream of the current device as a void* (the raw query: torch.cuda.current_stream() builds a
+    Stream object and costs ~15 us per call, several times per step)."""
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def ptr(t):
@@ -118,7 +120,7 @@ class Grid(object):
         self.edges_y = bin_edges(limXY[2], limXY[3], self.ny)
         self.edges_v = bin_edges(limV[0], limV[1], self.nv) if self.nv else None
         self.handle = ctypes.c_void_p()
-        self._mesh_np = self._mesh_dev = None
+        self._mesh_np = self._mesh_dev = self._centres = None
         ex, ey = _lib.doubles(self.edges_x), _lib.doubles(self.edges_y)
         ev = _lib.doubles(self.edges_v) if self.nv else None
         with torch.cuda.device(self.device):
@@ -159,12 +161,14 @@ class Grid(object):
 
     def centres(self):
         """Pixel centres (grid.py:141-142, :247-249); fresh arrays, the caller may keep them."""
-        px = np.linspace(self.limXY[0], self.limXY[1], self.nx)
-        py = np.linspace(self.limXY[2], self.limXY[3], self.ny)
-        pv = np.linspace(self.limV[0], self.limV[1], self.nv) if self.nv else None
-        return px, py, pv
+        if self._centres is None:
+            px = np.linspace(self.limXY[0], self.limXY[1], self.nx)
+            py = np.linspace(self.limXY[2], self.limXY[3], self.ny)
+            pv = np.linspace(self.limV[0], self.limV[1], self.nv) if self.nv else None
+            self._centres = (px, py, pv)
+        return tuple(None if a is None else a.copy() for a in self._centres)
 
-    def mesh(self, want_torch):
+    def mesh(self, want_torch, share=False):
         """gridX, gridY of the reference (np.meshgrid of the centres, (nY, nX)).  The device copy is
         made once per grid: a per-call pageable upload would stall the stream."""
         if self._mesh_np is None:
@@ -174,6 +178,8 @@ class Grid(object):
             return self._mesh_np[0].copy(), self._mesh_np[1].copy()
         if self._mesh_dev is None:
             self._mesh_dev = tuple(torch.from_numpy(a).to(self.device) for a in self._mesh_np)
+        if share:                     # read-only by convention (two clones per call cost two kernel launches)
+            return self._mesh_dev
         return self._mesh_dev[0].clone(), self._mesh_dev[1].clone()
 
     def __del__(self):
@@ -466,6 +472,14 @@ def finalize_cube(grid, cube, acc, scales, sums=0):
     return out
 
 
+def sum_chunks(chunks, nchunks, per, acc):
+    """pnm_sum_chunks: ``chunks`` holds nchunks arrays of ``per`` accumulator elements back to back -> their sum, added
+    in index order."""
+    out = torch.empty(per, dtype=acc.dtype, device=chunks.device)
+    _lib.call("pnm_sum_chunks", ptr(chunks), int(nchunks), int(per), acc.code, ptr(out), stream_ptr())
+    return out
+
+
 def slab_sums(grid, slabs, g0, g1, acc):
     """pnm_slab_sums: this rank's share of (sum w, sum w*d, sum w*d*d) per pixel from the record slabs [g0, g1) it
     holds (``slabs`` starts at slab g0) -> (3, nx*ny) tensor of the accumulator type."""
@@ -517,12 +531,24 @@ def gaussian_support(sig_a, sig_b):
     return s + 1 - s % 2
 
 
+_TAPS_CACHE = {}
+
+
 def gaussian_taps(sigma_pix, support):
-    """Normalised 1-D factor of the (separable) truncated 2-D Gaussian, float64 on the host."""
-    half = (support - 1) // 2
-    i = np.arange(-half, half + 1, dtype=np.float64)
-    g = np.exp(-0.5 * (i / sigma_pix) ** 2)
-    return g / g.sum()
+    """Normalised 1-D factor of the (separable) truncated 2-D Gaussian, float64 on the host (cached: a pipeline
+    smooths every step with the same widths)."""
+    key = (float(sigma_pix), int(support))
+    g = _TAPS_CACHE.get(key)
+    if g is None:
+        half = (support - 1) // 2
+        i = np.arange(-half, half + 1, dtype=np.float64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g = np.exp(-0.5 * (i / sigma_pix) ** 2)
+            g = g / g.sum()
+        if len(_TAPS_CACHE) > 64:
+            _TAPS_CACHE.clear()
+        _TAPS_CACHE[key] = g
+    return g.copy()
 
 
 def smooth_cube(cube, taps_axis0, taps_axis1):

@@ -27,11 +27,20 @@ class LOSVD(object):
         self.stepx = np.average(np.diff(_np(self.binx)))
         self.stepy = np.average(np.diff(_np(self.biny)))
         self.losvd = losvd
-        if err_losvd is None:
-            err_losvd = np.full(tuple(self.losvd.shape[:2]), None)
-        self.err_losvd = err_losvd
+        self._err_losvd = err_losvd          # None: the reference's (nX, nY) array of None, built on first access
         self.fwhmx = fwhmx
         self.fwhmy = fwhmy
+
+    @property
+    def err_losvd(self):
+        """Uncertainties of the LOSVDs; an (nX, nY) object array of None when there are none (pynmap/losvd.py:33-35)."""
+        if self._err_losvd is None:
+            self._err_losvd = np.full(tuple(self.losvd.shape[:2]), None)
+        return self._err_losvd
+
+    @err_losvd.setter
+    def err_losvd(self, value):
+        self._err_losvd = value
 
     @property
     def extent(self):
@@ -48,7 +57,9 @@ class LOSVD(object):
         return t.contiguous(), want_torch
 
     def _has_errors(self):
-        e = self.err_losvd
+        e = self._err_losvd
+        if e is None:
+            return False
         if isinstance(e, torch.Tensor):
             return True
         return e[0, 0] is not None
@@ -144,7 +155,10 @@ class LOSVD(object):
             conv_fwhmy = 0.
             reached_fwhmy = self.fwhmy
 
+        # the reference deep-copies (losvd.py:118): the new object shares nothing with this one -- the coordinate arrays
+        # are copied here, the cube and its uncertainties are replaced below
         closvd = copy.copy(self)
+        closvd.binx, closvd.biny, closvd.binv = (copy.deepcopy(a) for a in (self.binx, self.biny, self.binv))
         print("LOSVD FWHM: XLOS[{0}] YLOS[{1}]".format(self.fwhmx, self.fwhmy))
         print("Starting the Convolution to reach FWHM: XCLOS[{0}] YCLOS[{1}]".format(
               reached_fwhmx, reached_fwhmy))
@@ -163,7 +177,7 @@ class LOSVD(object):
             ecube, e_torch = self._cube_on_device(self.err_losvd)
             closvd.err_losvd = engine.to_output(engine.smooth_cube(ecube, taps_axis0, taps_axis1), e_torch)
         else:
-            closvd.err_losvd = self.err_losvd.copy()     # (nX, nY) array of None: nothing deep to copy
+            closvd._err_losvd = None                     # a fresh (nX, nY) array of None on first access
 
         closvd.fwhmx = reached_fwhmx
         closvd.fwhmy = reached_fwhmy

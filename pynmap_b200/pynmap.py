@@ -82,6 +82,25 @@ class SnapMap(object):
         return None
 
 
+class PendingProjection(object):
+    """What snapshot.project(deferred=True) returns: the scatter kernel has been launched; ``result()`` launches the
+    reduction over ranks (if any) and the finalisation, once, and returns (SnapMap, LOSVD)."""
+
+    def __init__(self, snap, grid, maps, cube, sums, acc, scales, reducer, token):
+        self._args = (snap, grid, maps, cube, sums, acc, scales, reducer, token)
+        self._out = None
+
+    def result(self):
+        if self._args is not None:
+            snap, grid, maps, cube, sums, acc, scales, reducer, token = self._args
+            self._args = None
+            if token is not None:
+                self._out = snap._project_post_slabs(grid, cube, acc, scales, reducer, token)
+            else:
+                self._out = snap._project_post(grid, maps, cube, sums, acc, scales, reducer)
+        return self._out
+
+
 class snapshot(object):
     """N-body snapshot (pynmap/pynmap.py:99-474)."""
 
@@ -406,8 +425,8 @@ class snapshot(object):
             entry = self._cube_plans[key] = (entry[0], grid, wkey)
         return entry[0]
 
-    def _mesh(self, grid):
-        return grid.mesh(self.output == "torch")
+    def _mesh(self, grid, share=False):
+        return grid.mesh(self.output == "torch", share)
 
     @staticmethod
     def _mask_arg(kwargs, mode):
@@ -547,7 +566,7 @@ class snapshot(object):
     # ------------------------------------------------------------------ additions (single read)
     def project(self, weights=None, weight_name=None, limXY=default_limXY, nXY=default_npoint,
                 limV=default_limV, nV=default_nVpoint, accumulate="f64", reducer=None, post_stream=None,
-                privatise=None):
+                privatise=None, deferred=False):
         """velocity_moments + create_losvds from ONE pass over the particles: returns
         (SnapMap, LOSVD) identical to calling the two methods separately.  The map's sum of
         weights is recovered from the cube (plus an out-of-range remainder), which saves one
@@ -557,6 +576,11 @@ class snapshot(object):
         shared-memory privatised kernel (csrc/pnm_cube.cuh; accumulate='f64' then rounds the privatised terms to
         2^-25 of the typical term, accumulate='fixed' uses coarser scales -- see engine.cube_fixed_scales); False
         forces the plain reduction kernel.
+
+        ``deferred=True``: only the scatter kernel (and, with a slab reducer, the start of the exchange between ranks)
+        is launched; returns a PendingProjection whose ``result()`` launches the rest and returns (SnapMap, LOSVD).
+        Calling ``result()`` after the NEXT project(deferred=True) lets the exchange of this step overlap the next
+        scatter kernel (sharded.PeerSlabReducer).
 
         ``post_stream``: a torch.cuda.Stream on which everything AFTER the scatter kernel runs
         (replica fold, the reduce over ranks, finalisation).  The scatter of the next call then
@@ -601,9 +625,15 @@ class snapshot(object):
             if plan is not None and not engine.cube_scales_ok(scales):
                 plan = None
         self.last_fixed_scales = scales        # (what a checker needs to reproduce the int64 sums)
+        if post_stream is not None and (deferred or hasattr(reducer, "acquire")):
+            raise ValueError("post_stream cannot be combined with deferred=True or a reducer that owns its accumulators "
+                             "(sharded.PeerSlabReducer): use project(deferred=True)")
         if post_stream is None:
-            maps, cube = self._run_fused(grid, w, sums, acc, scales, plan=plan, slab_multiple=slab_multiple)
-            return self._project_post(grid, maps, cube, sums, acc, scales, reducer)
+            recycled = (None, reducer.acquire(grid, acc)) if slabs and hasattr(reducer, "acquire") else None
+            maps, cube = self._run_fused(grid, w, sums, acc, scales, plan=plan, slab_multiple=slab_multiple, recycled=recycled)
+            token = reducer.begin(cube, grid, acc) if slabs else None
+            pending = PendingProjection(self, grid, maps, cube, sums, acc, scales, reducer, token)
+            return pending if deferred else pending.result()
         # pipelined: the accumulators are recycled -- cleared on the post-processing stream once their results are
         # out, so that no memset sits between two scatter kernels on the caller's stream
         pool = self._acc_pool.setdefault((id(grid), sums, acc.code, slab_multiple), [])
@@ -651,7 +681,7 @@ class snapshot(object):
     def _project_post(self, grid, maps, cube, sums, acc, scales, reducer):
         """Everything after the scatter of project(): fold + reduce over ranks, finalisation."""
         if getattr(reducer, "scatter_slabs", False):
-            return self._project_post_slabs(grid, cube, acc, scales, reducer)
+            return self._project_post_slabs(grid, cube, acc, scales, reducer, reducer.begin(cube, grid, acc))
         if reducer is not None:
             if not sums & _lib.CUBE_MOMENTS:                   # (the interleaved layout has a single map replica)
                 engine.fold_maps(grid, maps, acc, clear=False) # single-use accumulators: nothing adds to them again
@@ -668,15 +698,15 @@ class snapshot(object):
         mylosvd.PAs, mylosvd.inclinations = self.PAs, self.inclinations
         return newmap, mylosvd
 
-    def _project_post_slabs(self, grid, cube, acc, scales, reducer):
+    def _project_post_slabs(self, grid, cube, acc, scales, reducer, token):
         """Sharded post-processing (sharded.SlabReducer): reduce-scatter of the record slabs, every rank finalises
         its own velocity bins; the maps come from an all-reduce of the per-rank partial sums (3 values per pixel).
         -> (SnapMap, LOSVD of this rank's velocity bins) on every rank."""
         g0, g1 = reducer.slab_range(grid)
-        mine = reducer.scatter(cube, grid)
+        mine = reducer.finish(token)
         sums3 = reducer.all_sum(engine.slab_sums(grid, mine, g0, g1, acc))
         M, V, S = (self._out(t) for t in engine.finalize_sums(grid, sums3, acc, scales))
-        X, Y = self._mesh(grid)
+        X, Y = self._mesh(grid, share=True)
         newmap = SnapMap(name="Velocity moments", input_dic={"X": X, "Y": Y, "V": V, "M": M, "S": S,
                                                               "PAs": self.PAs, "inclinations": self.inclinations})
         px, py, pv = grid.centres()

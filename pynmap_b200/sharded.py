@@ -6,8 +6,12 @@ SUM of those partial grids -- `torch.distributed.reduce` (NCCL over NVLink on th
 in the CPU tests).  With int64 fixed-point accumulators the reduced grids are bit-identical for
 any number of ranks, because integer addition is associative.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 ALIGN = 8   # particles: keeps every shard's base pointer 32-byte aligned for float32 arrays
 
@@ -98,6 +102,14 @@ class SlabReducer(GridReducer):
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
 
+    # two-phase form (snapshot.project(deferred=True)): ``begin`` right after the scatter kernel has been launched,
+    # ``finish`` when the rank's slabs of the total are wanted.  Here the collective simply runs in ``finish``.
+    def begin(self, acc_padded, grid, acc):
+        return (acc_padded, grid)
+
+    def finish(self, token):
+        return self.scatter(*token)
+
     def gather_losvd(self, local_cube, grid, dst=None):
         """(nX, nY, own bins) float64 cubes of all ranks -> the whole (nX, nY, nV) cube on rank ``dst`` (None: on every
         rank); other ranks get None."""
@@ -110,3 +122,97 @@ class SlabReducer(GridReducer):
             return None
         parts = parts.reshape((self.world,) + tuple(pad.shape))
         return parts.permute(1, 2, 0, 3).reshape(grid.nx, grid.ny, self.world * 2 * c)[:, :, :grid.nv].contiguous()
+
+
+class PeerSlabReducer(SlabReducer):
+    """SlabReducer whose reduce-scatter uses no SMs and no NCCL kernel: the accumulators live in symmetric memory
+    (torch.distributed._symmetric_memory: every rank can address every rank's buffer over NVLink), and after a
+    device-side barrier every rank PULLS its own chunk of every rank's partial grid with the copy engines
+    (cudaMemcpyAsync peer copies on a side stream) into a local staging area; ``finish`` sums the staged chunks in rank
+    order (pnm_sum_chunks -- deterministic, and exact for int64).  The scatter kernel is persistent with one CTA per SM,
+    so nothing that needs SMs can run next to it (profiles/r02_timeline_*.log): the copy engines can.  With
+    ``snapshot.project(deferred=True)`` the pulls of step k overlap the scatter kernel of step k + 1:
+
+        pending = snap.project(..., reducer=r, deferred=True)      # scatter k, barrier, pulls start
+        nxt = snap.project(..., reducer=r, deferred=True)          # scatter k + 1 runs while step k's chunks arrive
+        vmap, losvd = pending.result()                             # sum of the staged chunks, finalisation, ...
+
+    Buffers: ``nbuf`` (>= 2) accumulators used round-robin + two staging areas, per (size, dtype).  An accumulator is
+    cleared after the barrier of the FOLLOWING step, when every rank has finished pulling from it."""
+
+    def __init__(self, group=None, nbuf=2, barrier_timeout_ms=60000):
+        super().__init__(group)
+        import torch.distributed._symmetric_memory as symm
+        if dist.get_backend(self.group) != "nccl":
+            raise RuntimeError("PeerSlabReducer needs CUDA devices with peer access (nccl process group)")
+        self._symm = symm
+        self._group_name = (self.group if self.group is not None else dist.group.WORLD).group_name
+        self.nbuf = max(2, int(nbuf))
+        self.timeout_ms = int(barrier_timeout_ms)
+        self._rings = {}
+        self._copy_stream = torch.cuda.Stream()
+
+    def _ring(self, numel, dtype, device):
+        key = (int(numel), dtype)
+        ring = self._rings.get(key)
+        if ring is None:                     # collective: every rank creates its rings in the same order
+            bufs, handles = [], []
+            for _ in range(self.nbuf):
+                t = self._symm.empty(int(numel), dtype=dtype, device=device)
+                handles.append(self._symm.rendezvous(t, self._group_name))
+                t.zero_()
+                bufs.append(t)
+            stage = [torch.empty(int(numel), dtype=dtype, device=device) for _ in range(2)]
+            ring = self._rings[key] = dict(bufs=bufs, handles=handles, stage=stage, next=0, step=0, pending=None, pulled=None)
+        return ring
+
+    def acquire(self, grid, acc):
+        """A zeroed, padded accumulator in symmetric memory for the next scatter (round-robin)."""
+        ring = self._ring(self.chunk_slabs(grid) * self.world * grid.slab_elems, acc.dtype, grid.device)
+        i = ring["next"]
+        ring["next"] = (i + 1) % self.nbuf
+        if ring["pending"] is not None and ring["bufs"][i].data_ptr() == ring["pending"].data_ptr():
+            raise RuntimeError("PeerSlabReducer: accumulator still in use (call result() of the pending projection "
+                               "before starting more than %d others)" % (self.nbuf - 1))
+        return ring["bufs"][i]
+
+    def begin(self, acc_padded, grid, acc):
+        ring = self._ring(acc_padded.numel(), acc_padded.dtype, acc_padded.device)
+        idx = [b.data_ptr() for b in ring["bufs"]].index(acc_padded.data_ptr())
+        handle = ring["handles"][idx]
+        per = self.chunk_slabs(grid) * grid.slab_elems
+        cur = torch.cuda.current_stream()
+        if ring["pulled"] is not None:
+            cur.wait_event(ring["pulled"])               # my pulls of the previous step are done before I say so
+        ring["handles"][0].barrier(channel=0, timeout_ms=self.timeout_ms)    # every rank: scatter done, previous pulls done
+        if ring["pending"] is not None:
+            ring["pending"].zero_()                      # nobody reads the previous accumulator any more
+        ring["pending"] = acc_padded
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        stage = ring["stage"][ring["step"] % 2]
+        ring["step"] += 1
+        cs = self._copy_stream
+        cs.wait_event(ready)
+        # copy-engine pulls through the C ABI (cudaMemcpyAsync on the copy stream; a torch copy_ per chunk under a
+        # stream context costs ~20 us of host time each): own chunk first, then the peers in ring order
+        esz = acc_padded.element_size()
+        peers = handle.buffer_ptrs
+        cs_ptr = ctypes.c_void_p(cs.cuda_stream)
+        for k in range(self.world):
+            p = (self.rank + k) % self.world
+            _lib.call("pnm_copy_async", ctypes.c_void_p(stage.data_ptr() + p * per * esz),
+                      ctypes.c_void_p(int(peers[p]) + self.rank * per * esz), per * esz, cs_ptr)
+        pulled = torch.cuda.Event()
+        pulled.record(cs)
+        ring["pulled"] = pulled
+        return (stage, pulled, per, acc)
+
+    def finish(self, token):
+        from . import engine
+        stage, pulled, per, acc = token
+        torch.cuda.current_stream().wait_event(pulled)
+        return engine.sum_chunks(stage, self.world, per, acc)
+
+    def scatter(self, acc_padded, grid):
+        raise RuntimeError("PeerSlabReducer works through begin() / finish() on accumulators from acquire()")

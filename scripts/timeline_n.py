@@ -8,6 +8,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--nccl-max-ctas", type=int, default=4)
 ap.add_argument("--reserve-sms", type=int, default=0)
 ap.add_argument("--steps", type=int, default=16)
+ap.add_argument("--reduce", default="scatter", choices=["scatter", "owner"])
 ap.add_argument("--particles", type=int, default=100_000_000)
 args = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
@@ -19,11 +20,11 @@ if args.nccl_max_ctas > 0:
 dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
 import pynmap_b200 as pnm, workloads
 from pynmap_b200 import engine
-from pynmap_b200.sharded import GridReducer
+from pynmap_b200.sharded import GridReducer, SlabReducer
 soa = workloads.make_snapshot(args.particles, bulge_fraction=0.2, seed=1235 + 1000 * rank, device="cuda")
 snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="torch")
 snap.rotate(PA=30., inclination=60.)
-reducer = GridReducer(reserve_sms=args.reserve_sms)
+reducer = (GridReducer if args.reduce == 'owner' else SlabReducer)(reserve_sms=args.reserve_sms)
 post = torch.cuda.Stream(priority=-1)
 sink = io.StringIO()
 marks = []          # (step, name, event)
@@ -33,6 +34,11 @@ class Timed(object):
     def __call__(self, *t):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(); out = self.inner(*t); b.record()
+        marks.append((counter[0], "reduce0", a)); marks.append((counter[0], "reduce1", b))
+        return out
+    def scatter(self, *t):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); out = self.inner.scatter(*t); b.record()
         marks.append((counter[0], "reduce0", a)); marks.append((counter[0], "reduce1", b))
         return out
 timed = Timed(reducer)
@@ -66,7 +72,7 @@ for s, name, e in marks:
 for r in range(world):
     dist.barrier()
     if r == rank and rank in (0, 1):
-        print("rank %d (ctas %d, reserved %d): step owner | scatter start..end | reduce start..end | post end   [ms from origin]" % (rank, args.nccl_max_ctas, args.reserve_sms))
+        print("rank %d (%s, ctas %d, reserved %d): step owner | scatter start..end | reduce start..end | post end   [ms from origin]" % (rank, args.reduce, args.nccl_max_ctas, args.reserve_sms))
         for s in sorted(rows):
             v = rows[s]
             print("  %3d  own=%d | %7.3f .. %7.3f | %7.3f .. %7.3f | %7.3f" % (s, s % world, v.get("scat0", -1), v.get("scat1", -1), v.get("reduce0", -1), v.get("reduce1", -1), v.get("post1", -1)), flush=True)

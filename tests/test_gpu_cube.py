@@ -287,7 +287,7 @@ def test_slab_finalisation_equals_whole_accumulator(env):
     rows = [soa[k] for k in range(6)]
     mat = on.rotation_matrix(np.float32(30.), np.float32(60.))
     sums = 31 | _lib.CUBE_MOMENTS
-    for nv in (33, 8, 1):
+    for nv in (33, 8, 2):
         grid = engine.get_grid(wl.LIM_XY, 40, 24, wl.LIM_V, nv)
         for mode in ("fixed", "f64"):
             acc = engine.AccMode(mode)
@@ -326,7 +326,8 @@ def test_project_through_slab_reducer_single_rank(env):
         scatter_slabs, world, rank, reserve_sms = True, 1, 0, 0
         def chunk_slabs(self, grid): return grid.record_slabs
         def slab_range(self, grid, rank=None): return 0, grid.record_slabs
-        def scatter(self, acc, grid): return acc
+        def begin(self, acc, grid, mode): return (acc, grid)
+        def finish(self, token): return token[0]
         def all_sum(self, t): return t
         def n_total(self, n_local): return n_local
         def reduce_max(self, *v): return v
@@ -341,6 +342,10 @@ def test_project_through_slab_reducer_single_rank(env):
         vm1, lv1 = snap.project(reducer=OneRank(), post_stream=stream, **kw)
         with (torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream())):
             sm1 = lv1.convolve_spatial(1.0, 1.0)
+        if stream is None:                                    # two-phase form: scatter now, the rest on demand
+            pend = snap.project(reducer=OneRank(), deferred=True, **kw)
+            assert pend.result() is pend.result()
+            assert tsame(pend.result()[0].V, vm0.V) and torch.equal(pend.result()[1].losvd, lv0.losvd)
         torch.cuda.synchronize()
         assert lv1.vrange == (0, 37)
         assert tsame(vm1.M, vm0.M) and tsame(vm1.V, vm0.V) and tsame(vm1.S, vm0.S)
