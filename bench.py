@@ -18,7 +18,6 @@ import io
 import json
 import os
 import sys
-import threading
 import time
 
 import numpy as np
@@ -150,45 +149,73 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ clocks
-class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+class ClockSampler(object):
+    """Samples the SM clock and the throttle reasons of one GPU while the timed region runs -- from a CHILD PROCESS
+    (`nvidia-smi --query-gpu ... -lms 5`), not a thread: a polling thread shares the GIL with the launching loop, and in
+    a sharded run a launch loop that loses a few milliseconds stalls every rank at the next device-side barrier."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
-    def __init__(self, index, period=0.005):
-        super().__init__(daemon=True)
-        self.index, self.period = index, period
-        self.samples, self.mask, self.max_mhz, self.ok = [], 0, None, False
-        self._stop_evt = threading.Event()
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
-            self.ok = True
-        except Exception:
-            self.ok = False
-
-    def run(self):
-        if not self.ok:
+    def __init__(self, index, period_ms=5):
+        import shutil
+        import subprocess
+        self.proc, self.ok = None, False
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
             return
-        get_reasons = getattr(self.nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
-            getattr(self.nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
-        while not self._stop_evt.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                self.mask |= int(get_reasons(self.h))
+        try:
+            self.proc = subprocess.Popen(
+                [exe, "-i", str(index), "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                 "--format=csv,noheader,nounits", "-lms", str(period_ms)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.first = self.proc.stdout.readline()         # blocks until the child is polling (driver start-up)
+            self.ok = bool(self.first.strip())
+            self.nvml = None
+            try:                                             # one more sample from this process, see sample_now()
+                import pynvml
+                pynvml.nvmlInit()
+                self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
             except Exception:
                 pass
-            time.sleep(self.period)
+            self.extra = []
+        except Exception:
+            self.proc = None
+
+    def sample_now(self):
+        """One NVML sample taken by the launching thread itself (called right after the last launch of the timed
+        region, while the GPU is still working through the queue)."""
+        if self.ok and self.nvml is not None:
+            try:
+                nv, h = self.nvml
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.extra.append((float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), int(get(h))))
+            except Exception:
+                pass
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=2)
-        reasons = [name for bit, name in self.REASONS.items() if self.mask & bit]
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": reasons, "samples": len(self.samples)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        samples, mask, max_mhz = [c for c, _ in self.extra], 0, None
+        for _, m in self.extra:
+            mask |= m
+        lines = out.splitlines()
+        for line in (lines if lines else [self.first]):      # (the first sample was taken before the timed region)
+            parts = [p.strip() for p in line.split(",")]
+            try:
+                samples.append(float(parts[0]))
+                max_mhz = float(parts[1])
+                mask |= int(parts[2], 16)
+            except Exception:
+                continue
+        reasons = [name for bit, name in self.REASONS.items() if mask & bit]
+        return {"sm_mhz": float(np.median(samples)) if samples else None, "sm_max_mhz": max_mhz,
+                "reasons": reasons, "samples": len(samples), "sampler": "nvidia-smi -lms 5 (child process)"}
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -390,8 +417,13 @@ def run_b200(args):
     for _ in range(max(3, args.warmup)):
         step()
     fence()
-    sampler = ClockSampler(local)
-    sampler.start()
+    # the ranks of a sharded run meet at a device-side barrier every step: a cyclic-GC pause of the Python host of any
+    # rank (milliseconds with torch loaded) stalls all of them, so the collector rests during the timed region
+    import gc
+    gc.collect()
+    gc.disable()
+    sampler = ClockSampler(local) if rank == 0 else None     # rank 0's GPU stands for the node (one line is printed)
+    fence()
     engine.KERNEL_TIMER = timer = engine.KernelTimer()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
@@ -399,13 +431,16 @@ def run_b200(args):
     for _ in range(args.steps):
         step()
     drain()                                                 # (deferred mode: the last step's finalisation is inside the timed region)
+    if sampler is not None:
+        sampler.sample_now()
     enqueue_s[0] = time.perf_counter() - enqueue_s[0]       # host time spent launching the K steps (no synchronisation inside)
     if post is not None:
         torch.cuda.current_stream().wait_stream(post)      # the last step's post-processing is inside the timed region
     t1.record()
     fence()
+    gc.enable()
     engine.KERNEL_TIMER = None
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

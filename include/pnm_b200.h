@@ -278,6 +278,10 @@ int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t
 /* cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, stream): device pointers of this or of a peer device (unified
  * addressing) -- the copy-engine pull of the peer-to-peer reduce-scatter.                                          */
 int pnm_copy_async(void* dst, const void* src, int64_t nbytes, void* stream);
+int pnm_zero_async(void* dst, int64_t nbytes, void* stream);      /* cudaMemsetAsync(dst, 0, nbytes, stream) */
+/* out[i] = sum over r < nptrs of ptrs_host[r][i] (8-byte accumulator elements; index order): the arrays may live on peer
+ * devices mapped into this process (symmetric memory) -- a one-shot all-reduce of small arrays over NVLink loads.    */
+int pnm_sum_peers(const void* const* ptrs_host, int32_t nptrs, int64_t n, int acc_mode, void* out, void* stream);
 int pnm_sum_chunks(const void* chunks, int32_t nchunks, int64_t per, int acc_mode, void* out, void* stream);
 int pnm_slab_sums(const pnm_grid* g, const void* slabs, int32_t g0, int32_t g1, int acc_mode, void* sums3, void* stream);
 int pnm_finalize_sums(const pnm_grid* g, const void* sums3, int acc_mode, const double* scales3_host,

@@ -64,6 +64,8 @@ _SIGNATURES = {
                                  POINTER(c_double), c_int32, POINTER(c_double), c_int32, _P, _P, _P, _P]),
     "pnm_host_release": (c_int, []),
     "pnm_copy_async": (c_int, [_P, _P, c_int64, _P]),
+    "pnm_zero_async": (c_int, [_P, c_int64, _P]),
+    "pnm_sum_peers": (c_int, [POINTER(_P), c_int32, c_int64, c_int, _P, _P]),
     "pnm_sum_chunks": (c_int, [_P, c_int32, c_int64, c_int, _P, _P]),
     "pnm_slab_sums": (c_int, [_P, _P, c_int32, c_int32, c_int, _P, _P]),
     "pnm_finalize_sums": (c_int, [_P, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),

@@ -416,6 +416,31 @@ int pnm_copy_async(void* dst, const void* src, int64_t nbytes, void* stream) {
     return PNM_OK;
 }
 
+int pnm_zero_async(void* dst, int64_t nbytes, void* stream) {
+    if (nbytes < 0 || (nbytes > 0 && !dst)) return fail(PNM_EINVAL, "pnm_zero_async: bad argument");
+    if (nbytes == 0) return PNM_OK;
+    PNM_CUDA(cudaMemsetAsync(dst, 0, (size_t)nbytes, as_stream(stream)));
+    return PNM_OK;
+}
+
+int pnm_sum_peers(const void* const* ptrs_host, int32_t nptrs, int64_t n, int acc_mode, void* out, void* stream) {
+    if (!ptrs_host || !out || nptrs < 1 || nptrs > PNM_MAX_PEERS || n < 0) return fail(PNM_EINVAL, "pnm_sum_peers: bad argument (at most %d arrays)", PNM_MAX_PEERS);
+    if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_sum_peers: acc_mode %d", acc_mode);
+    pnm::PeerPtrs src;
+    memset(&src, 0, sizeof(src));
+    src.n = nptrs;
+    for (int r = 0; r < nptrs; ++r) {
+        if (!ptrs_host[r]) return fail(PNM_EINVAL, "pnm_sum_peers: null array %d", r);
+        src.p[r] = ptrs_host[r];
+    }
+    if (n == 0) return PNM_OK;
+    const int grid = (int)((n + 255) / 256);
+    if (acc_mode == PNM_ACC_F64) pnm::k_sum_peers<PNM_ACC_F64><<<grid, 256, 0, as_stream(stream)>>>(src, n, out);
+    else pnm::k_sum_peers<PNM_ACC_FIXED><<<grid, 256, 0, as_stream(stream)>>>(src, n, out);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
 int pnm_sum_chunks(const void* chunks, int32_t nchunks, int64_t per, int acc_mode, void* out, void* stream) {
     if (!chunks || !out || nchunks < 1 || per < 0) return fail(PNM_EINVAL, "pnm_sum_chunks: bad argument");
     if (acc_mode != PNM_ACC_F64 && acc_mode != PNM_ACC_FIXED) return fail(PNM_EINVAL, "pnm_sum_chunks: acc_mode %d", acc_mode);

@@ -1,6 +1,9 @@
 // pnm_post.cuh -- everything after the scatter: finalisation (K5), smoothing (K4), cube moments (f1),
 // plus the materialising rotation (K1) and the abs-max reduction used to size fixed-point scales.
 #pragma once
+#ifndef PNM_MAX_PEERS
+#define PNM_MAX_PEERS 16
+#endif
 #include "pnm_common.cuh"
 #include "pnm_bin.cuh"
 
@@ -238,6 +241,23 @@ __global__ void __launch_bounds__(256) k_sum_chunks(const void* chunks, int nchu
             }
         }
     }
+}
+
+// out[i] = src[0][i] + src[1][i] + ... (pointers into this device's or peer devices' memory; index order)
+struct PeerPtrs { const void* p[PNM_MAX_PEERS]; int n; };
+template <int ACC>
+__global__ void __launch_bounds__(256) k_sum_peers(const PeerPtrs src, int64_t n, void* out) {
+    using A = typename AccT<ACC>::type;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    A v[PNM_MAX_PEERS];
+#pragma unroll
+    for (int r = 0; r < PNM_MAX_PEERS; ++r) v[r] = r < src.n ? reinterpret_cast<const A*>(src.p[r])[i] : A(0);   // all loads in flight
+    A t = 0;
+#pragma unroll
+    for (int r = 0; r < PNM_MAX_PEERS; ++r)
+        if (r < src.n) { if (ACC == PNM_ACC_F64) t = (A)__dadd_rn((double)t, (double)v[r]); else t += v[r]; }
+    reinterpret_cast<A*>(out)[i] = t;
 }
 
 template <int ACC>

@@ -480,10 +480,20 @@ def sum_chunks(chunks, nchunks, per, acc):
     return out
 
 
-def slab_sums(grid, slabs, g0, g1, acc):
+def sum_peers(ptrs, n, acc, device):
+    """pnm_sum_peers: arrays of ``n`` accumulator elements at the device addresses ``ptrs`` (this device's or peers')
+    -> their sum, added in list order."""
+    out = torch.empty(n, dtype=acc.dtype, device=device)
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    _lib.call("pnm_sum_peers", arr, len(ptrs), int(n), acc.code, ptr(out), stream_ptr())
+    return out
+
+
+def slab_sums(grid, slabs, g0, g1, acc, out=None):
     """pnm_slab_sums: this rank's share of (sum w, sum w*d, sum w*d*d) per pixel from the record slabs [g0, g1) it
     holds (``slabs`` starts at slab g0) -> (3, nx*ny) tensor of the accumulator type."""
-    out = torch.empty((3, grid.nx * grid.ny), dtype=acc.dtype, device=grid.device)
+    if out is None:
+        out = torch.empty((3, grid.nx * grid.ny), dtype=acc.dtype, device=grid.device)
     _lib.call("pnm_slab_sums", grid.handle, ptr(slabs), int(g0), int(g1), acc.code, ptr(out), stream_ptr())
     return out
 

@@ -704,7 +704,7 @@ class snapshot(object):
         -> (SnapMap, LOSVD of this rank's velocity bins) on every rank."""
         g0, g1 = reducer.slab_range(grid)
         mine = reducer.finish(token)
-        sums3 = reducer.all_sum(engine.slab_sums(grid, mine, g0, g1, acc))
+        sums3 = reducer.map_sums(token, mine, grid, acc)
         M, V, S = (self._out(t) for t in engine.finalize_sums(grid, sums3, acc, scales))
         X, Y = self._mesh(grid, share=True)
         newmap = SnapMap(name="Velocity moments", input_dic={"X": X, "Y": Y, "V": V, "M": M, "S": S,

@@ -7,6 +7,7 @@ in the CPU tests).  With int64 fixed-point accumulators the reduced grids are bi
 any number of ranks, because integer addition is associative.
 """
 import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -110,6 +111,13 @@ class SlabReducer(GridReducer):
     def finish(self, token):
         return self.scatter(*token)
 
+    def map_sums(self, token, mine, grid, acc):
+        """Total (sum w, sum w*d, sum w*d*d) per pixel, (3, nx*ny) of the accumulator type, on every rank: the rank's
+        share from its own slabs of the total, all-reduced."""
+        from . import engine
+        g0, g1 = self.slab_range(grid)
+        return self.all_sum(engine.slab_sums(grid, mine, g0, g1, acc))
+
     def gather_losvd(self, local_cube, grid, dst=None):
         """(nX, nY, own bins) float64 cubes of all ranks -> the whole (nX, nY, nV) cube on rank ``dst`` (None: on every
         rank); other ranks get None."""
@@ -151,6 +159,14 @@ class PeerSlabReducer(SlabReducer):
         self.timeout_ms = int(barrier_timeout_ms)
         self._rings = {}
         self._copy_stream = torch.cuda.Stream()
+        self.peer_sums = os.environ.get("PNM_PEER_SUMS", "nccl") == "peer"    # map sums over peer memory or an NCCL all-reduce
+        self.trace = None                    # development: a list collects (name, timing event) pairs (scripts/timeline_n.py)
+
+    def _mark(self, name, stream):
+        if self.trace is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            self.trace.append((name, e))
 
     def _ring(self, numel, dtype, device):
         key = (int(numel), dtype)
@@ -163,7 +179,8 @@ class PeerSlabReducer(SlabReducer):
                 t.zero_()
                 bufs.append(t)
             stage = [torch.empty(int(numel), dtype=dtype, device=device) for _ in range(2)]
-            ring = self._rings[key] = dict(bufs=bufs, handles=handles, stage=stage, next=0, step=0, pending=None, pulled=None)
+            ring = self._rings[key] = dict(bufs=bufs, handles=handles, stage=stage, next=0, step=0, pending=None, pulled=None,
+                                           cleared=[None] * self.nbuf)
         return ring
 
     def acquire(self, grid, acc):
@@ -182,37 +199,69 @@ class PeerSlabReducer(SlabReducer):
         handle = ring["handles"][idx]
         per = self.chunk_slabs(grid) * grid.slab_elems
         cur = torch.cuda.current_stream()
+        self._mark("begin", cur)
         if ring["pulled"] is not None:
             cur.wait_event(ring["pulled"])               # my pulls of the previous step are done before I say so
         ring["handles"][0].barrier(channel=0, timeout_ms=self.timeout_ms)    # every rank: scatter done, previous pulls done
+        self._mark("barrier", cur)
         if ring["pending"] is not None:
             ring["pending"].zero_()                      # nobody reads the previous accumulator any more
-        ring["pending"] = acc_padded
+        self._mark("zeroed", cur)
         ready = torch.cuda.Event()
         ready.record(cur)
         stage = ring["stage"][ring["step"] % 2]
         ring["step"] += 1
         cs = self._copy_stream
+        cs_ptr = ctypes.c_void_p(cs.cuda_stream)
         cs.wait_event(ready)
+        ring["pending"] = acc_padded
         # copy-engine pulls through the C ABI (cudaMemcpyAsync on the copy stream; a torch copy_ per chunk under a
         # stream context costs ~20 us of host time each): own chunk first, then the peers in ring order
         esz = acc_padded.element_size()
         peers = handle.buffer_ptrs
-        cs_ptr = ctypes.c_void_p(cs.cuda_stream)
         for k in range(self.world):
             p = (self.rank + k) % self.world
             _lib.call("pnm_copy_async", ctypes.c_void_p(stage.data_ptr() + p * per * esz),
                       ctypes.c_void_p(int(peers[p]) + self.rank * per * esz), per * esz, cs_ptr)
         pulled = torch.cuda.Event()
         pulled.record(cs)
+        self._mark("pulled", cs)
         ring["pulled"] = pulled
         return (stage, pulled, per, acc)
 
     def finish(self, token):
         from . import engine
-        stage, pulled, per, acc = token
-        torch.cuda.current_stream().wait_event(pulled)
-        return engine.sum_chunks(stage, self.world, per, acc)
+        stage, pulled, per, acc = token[:4]
+        cur = torch.cuda.current_stream()
+        cur.wait_event(pulled)
+        self._mark("finish", cur)
+        out = engine.sum_chunks(stage, self.world, per, acc)
+        self._mark("summed", cur)
+        return out
+
+    def map_sums(self, token, mine, grid, acc):
+        """One-shot all-reduce over peer memory instead of an NCCL call: every rank writes its share of the per-pixel
+        sums into its symmetric buffer, a device-side barrier, then every rank adds the shares of all ranks in rank
+        order straight from peer memory (pnm_sum_peers: 8 x 0.4 MB of NVLink loads) -- the same bits on every rank."""
+        from . import engine
+        if not self.peer_sums:
+            return SlabReducer.map_sums(self, token, mine, grid, acc)
+        g0, g1 = self.slab_range(grid)
+        npix3 = 3 * grid.nx * grid.ny
+        key = ("shares", npix3, acc.dtype)
+        sh = self._rings.get(key)
+        if sh is None:
+            bufs, handles = [], []
+            for _ in range(2):
+                t = self._symm.empty(npix3, dtype=acc.dtype, device=grid.device)
+                handles.append(self._symm.rendezvous(t, self._group_name))
+                bufs.append(t)
+            sh = self._rings[key] = dict(bufs=bufs, handles=handles, step=0)
+        i = sh["step"] % 2               # double buffered: a rank may be one barrier ahead of the readers of the other buffer
+        sh["step"] += 1
+        engine.slab_sums(grid, mine, g0, g1, acc, out=sh["bufs"][i].view(3, -1))
+        sh["handles"][0].barrier(channel=1, timeout_ms=self.timeout_ms)
+        return engine.sum_peers([int(p) for p in sh["handles"][i].buffer_ptrs], npix3, acc, grid.device).view(3, -1)
 
     def scatter(self, acc_padded, grid):
         raise RuntimeError("PeerSlabReducer works through begin() / finish() on accumulators from acquire()")

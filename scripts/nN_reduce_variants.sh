@@ -11,10 +11,13 @@ run() {
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $port \
     bench.py --gpus $N --no-e2e --no-extras --no-cpu-baseline "$@" 2> gpurun_out/n${N}_last.err | grep '^{' >> $out || tail -20 gpurun_out/n${N}_last.err
 }
+if [ "$2" = "quick" ]; then
 run --steps 20 --warmup 5 --reduce peer
+else
+run --steps 20 --warmup 5 --reduce peer
+run --steps 20 --warmup 5 --no-parity --reduce peer
 run --steps 60 --warmup 5 --no-parity --reduce peer
-run --steps 60 --warmup 5 --no-parity --reduce scatter --no-pipeline --nccl-max-ctas 0
-run --steps 60 --warmup 5 --no-parity --reduce owner --nccl-max-ctas 0
+fi
 python - <<PY
 import json
 for l in open("$out"):

@@ -328,7 +328,9 @@ def test_project_through_slab_reducer_single_rank(env):
         def slab_range(self, grid, rank=None): return 0, grid.record_slabs
         def begin(self, acc, grid, mode): return (acc, grid)
         def finish(self, token): return token[0]
-        def all_sum(self, t): return t
+        def map_sums(self, token, mine, grid, acc):
+            from pynmap_b200 import engine
+            return engine.slab_sums(grid, mine, 0, grid.record_slabs, acc)
         def n_total(self, n_local): return n_local
         def reduce_max(self, *v): return v
 
