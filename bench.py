@@ -151,12 +151,12 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler(object):
     """Samples the SM clock and the throttle reasons of one GPU while the timed region runs -- from a CHILD PROCESS
-    (`nvidia-smi --query-gpu ... -lms 5`), not a thread: a polling thread shares the GIL with the launching loop, and in
+    (`nvidia-smi --query-gpu ... -lms 20`, plus one NVML read by the launching thread while the queue drains), not a thread: a polling thread shares the GIL with the launching loop, and in
     a sharded run a launch loop that loses a few milliseconds stalls every rank at the next device-side barrier."""
     REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
                0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
 
-    def __init__(self, index, period_ms=5):
+    def __init__(self, index, period_ms=20):
         import shutil
         import subprocess
         self.proc, self.ok = None, False
@@ -215,7 +215,7 @@ class ClockSampler(object):
                 continue
         reasons = [name for bit, name in self.REASONS.items() if mask & bit]
         return {"sm_mhz": float(np.median(samples)) if samples else None, "sm_max_mhz": max_mhz,
-                "reasons": reasons, "samples": len(samples), "sampler": "nvidia-smi -lms 5 (child process)"}
+                "reasons": reasons, "samples": len(samples), "sampler": "nvidia-smi -lms 20 (child process) + one NVML read after the last launch"}
 
 
 # ------------------------------------------------------------------------------------------ our arm

@@ -179,7 +179,9 @@ int pnm_finalize_cube(const pnm_grid* g, const void* acc_cube, int sums, int acc
  * cube_in/out/work: float64 [nx][ny][nv], three distinct buffers (work = scratch of the same
  * size, owned by the caller).  taps0_host act along array axis 0, taps1_host along axis 1 (odd
  * counts, already normalised, built on the host in float64).  Zero fill outside the array
- * (astropy convolve boundary='fill', fill_value=0).                                           */
+ * (astropy convolve boundary='fill', fill_value=0).  NaN voxels follow astropy's default
+ * nan_treatment='interpolate': an output with NaNs in its footprint is the kernel-weighted mean of
+ * the non-NaN samples (samples outside the array count as 0), or the input value if all are NaN. */
 int pnm_smooth_cube(const double* cube_in, double* cube_out, double* work,
                     int32_t nx, int32_t ny, int32_t nv,
                     const double* taps0_host, int32_t ntaps0,
@@ -278,7 +280,10 @@ int pnm_fit_gh(const double* cube, const double* err_dev, int64_t nspax, int32_t
 /* cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDefault, stream): device pointers of this or of a peer device (unified
  * addressing) -- the copy-engine pull of the peer-to-peer reduce-scatter.                                          */
 int pnm_copy_async(void* dst, const void* src, int64_t nbytes, void* stream);
-int pnm_zero_async(void* dst, int64_t nbytes, void* stream);      /* cudaMemsetAsync(dst, 0, nbytes, stream) */
+int pnm_zero_async(void* dst, int64_t nbytes, void* stream);
+/* the pulls of a peer-to-peer reduce-scatter in one call: for every rank p, chunk `rank` (chunk_bytes bytes) of the
+ * buffer at bases_host[p] (this device's or a peer's) -> stage + p * chunk_bytes; own buffer first, then ring order.  */
+int pnm_pull_chunks(void* stage, const void* const* bases_host, int32_t nranks, int32_t rank, int64_t chunk_bytes, void* stream);      /* cudaMemsetAsync(dst, 0, nbytes, stream) */
 /* out[i] = sum over r < nptrs of ptrs_host[r][i] (8-byte accumulator elements; index order): the arrays may live on peer
  * devices mapped into this process (symmetric memory) -- a one-shot all-reduce of small arrays over NVLink loads.    */
 int pnm_sum_peers(const void* const* ptrs_host, int32_t nptrs, int64_t n, int acc_mode, void* out, void* stream);

@@ -319,19 +319,26 @@ def gaussian_kernel2d(x_stddev, y_stddev):
 
 
 def convolve2d_fill0(img, ker):
-    """Direct 'same' convolution with zero fill (astropy.convolution.convolve defaults:
-    boundary='fill', fill_value=0, normalize_kernel=True) in float64."""
+    """Direct 'same' convolution with zero fill in float64 -- astropy.convolution.convolve with its defaults
+    boundary='fill', fill_value=0, nan_treatment='interpolate', normalize_kernel=True (restated from astropy's
+    documentation; astropy is absent -> parity unpinned): NaN samples are skipped and each output is divided by the
+    sum of the kernel values it used (the zero padding counts); an output with only NaN samples keeps the input."""
     img = np.asarray(img, dtype=np.float64)
     ker = np.asarray(ker, dtype=np.float64)
     ker = ker / ker.sum()
     ha, hb = ker.shape[0] // 2, ker.shape[1] // 2
     pad = np.zeros((img.shape[0] + 2 * ha, img.shape[1] + 2 * hb))
     pad[ha:ha + img.shape[0], hb:hb + img.shape[1]] = img
-    out = np.zeros_like(img)
+    good = ~np.isnan(pad)
+    vals = np.where(good, pad, 0.0)
+    top, bot = np.zeros_like(img), np.zeros_like(img)
     for a in range(ker.shape[0]):
         for b in range(ker.shape[1]):
-            out += ker[ker.shape[0] - 1 - a, ker.shape[1] - 1 - b] * pad[a:a + img.shape[0], b:b + img.shape[1]]
-    return out
+            k = ker[ker.shape[0] - 1 - a, ker.shape[1] - 1 - b]
+            top += k * vals[a:a + img.shape[0], b:b + img.shape[1]]
+            bot += k * good[a:a + img.shape[0], b:b + img.shape[1]]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(bot == 0.0, img, top / bot)
 
 
 def residual_fwhm(target, current):

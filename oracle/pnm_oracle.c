@@ -179,24 +179,27 @@ void pnmo_finalize_vmaps(const void* acc_maps, const void* acc_cube, int nx, int
     }
 }
 
-/* ---- losvd.py:127-135: astropy convolve(slice, Gaussian2DKernel): direct 'same' convolution,
- * zero fill, kernel ker[ka][kb] (ka along cube axis 0, kb along axis 1), already normalised ---- */
+/* ---- losvd.py:127-135: astropy convolve(slice, Gaussian2DKernel) with its defaults boundary='fill', fill_value=0,
+ * nan_treatment='interpolate', normalize_kernel=True (astropy/convolution/convolve.py and its C loop, restated from
+ * the documentation: astropy is absent here): direct 'same' convolution over the zero-padded slice; NaN samples are
+ * skipped and every output is divided by the sum of the kernel values it used (padding counts: 0 is a number); an
+ * output all of whose samples are NaN keeps the input value.  ker[ka][kb] (ka along cube axis 0), already normalised. */
 void pnmo_smooth_cube(const double* in, double* out, int nx, int ny, int nv, const double* ker, int ka, int kb) {
     const int ha = ka / 2, hb = kb / 2;
     for (int ix = 0; ix < nx; ++ix)
         for (int iy = 0; iy < ny; ++iy)
             for (int k = 0; k < nv; ++k) {
-                double acc = 0.0;
+                double top = 0.0, bot = 0.0;
                 for (int a = 0; a < ka; ++a) {
                     int sx = ix + ha - a;                 /* true convolution: kernel flipped */
-                    if (sx < 0 || sx >= nx) continue;
                     for (int b = 0; b < kb; ++b) {
                         int sy = iy + hb - b;
-                        if (sy < 0 || sy >= ny) continue;
-                        acc += ker[a * kb + b] * in[((int64_t)sx * ny + sy) * nv + k];
+                        double val = 0.0;
+                        if (sx >= 0 && sx < nx && sy >= 0 && sy < ny) val = in[((int64_t)sx * ny + sy) * nv + k];
+                        if (!isnan(val)) { top += ker[a * kb + b] * val; bot += ker[a * kb + b]; }
                     }
                 }
-                out[((int64_t)ix * ny + iy) * nv + k] = acc;
+                out[((int64_t)ix * ny + iy) * nv + k] = bot == 0.0 ? in[((int64_t)ix * ny + iy) * nv + k] : top / bot;
             }
 }
 

@@ -65,6 +65,7 @@ _SIGNATURES = {
     "pnm_host_release": (c_int, []),
     "pnm_copy_async": (c_int, [_P, _P, c_int64, _P]),
     "pnm_zero_async": (c_int, [_P, c_int64, _P]),
+    "pnm_pull_chunks": (c_int, [_P, POINTER(_P), c_int32, c_int32, c_int64, _P]),
     "pnm_sum_peers": (c_int, [POINTER(_P), c_int32, c_int64, c_int, _P, _P]),
     "pnm_sum_chunks": (c_int, [_P, c_int32, c_int64, c_int, _P, _P]),
     "pnm_slab_sums": (c_int, [_P, _P, c_int32, c_int32, c_int, _P, _P]),

@@ -416,6 +416,21 @@ int pnm_copy_async(void* dst, const void* src, int64_t nbytes, void* stream) {
     return PNM_OK;
 }
 
+int pnm_pull_chunks(void* stage, const void* const* bases_host, int32_t nranks, int32_t rank, int64_t chunk_bytes, void* stream) {
+    if (!stage || !bases_host || nranks < 1 || nranks > PNM_MAX_PEERS || rank < 0 || rank >= nranks || chunk_bytes < 0)
+        return fail(PNM_EINVAL, "pnm_pull_chunks: bad argument (at most %d ranks)", PNM_MAX_PEERS);
+    if (chunk_bytes == 0) return PNM_OK;
+    // chunk `rank` of every rank's buffer -> stage[p]; own buffer first, then the peers in ring order (every link busy)
+    for (int k = 0; k < nranks; ++k) {
+        const int p = (rank + k) % nranks;
+        if (!bases_host[p]) return fail(PNM_EINVAL, "pnm_pull_chunks: null base %d", p);
+        PNM_CUDA(cudaMemcpyAsync(static_cast<char*>(stage) + (size_t)p * chunk_bytes,
+                                 static_cast<const char*>(bases_host[p]) + (size_t)rank * chunk_bytes, (size_t)chunk_bytes,
+                                 cudaMemcpyDefault, as_stream(stream)));
+    }
+    return PNM_OK;
+}
+
 int pnm_zero_async(void* dst, int64_t nbytes, void* stream) {
     if (nbytes < 0 || (nbytes > 0 && !dst)) return fail(PNM_EINVAL, "pnm_zero_async: bad argument");
     if (nbytes == 0) return PNM_OK;
@@ -534,8 +549,9 @@ int pnm_smooth_cube(const double* cube_in, double* cube_out, double* work, int32
     const int64_t total = (int64_t)nx * ny * nv;
     const int grid = grid_for(total, 256, 8);
     // one thread per kSmoothOut outputs along the convolved axis
-    pnm::k_smooth_axis<0><<<grid, 256, 0, as_stream(stream)>>>(cube_in, work, nx, ny, nv, t0);
-    pnm::k_smooth_axis<1><<<grid, 256, 0, as_stream(stream)>>>(work, cube_out, nx, ny, nv, t1);
+    // (second pass: outputs with a NaN in their footprint are redone in 2-D with astropy's nan_treatment='interpolate')
+    pnm::k_smooth_axis<0><<<grid, 256, 0, as_stream(stream)>>>(cube_in, work, nx, ny, nv, t0, nullptr, t0);
+    pnm::k_smooth_axis<1><<<grid, 256, 0, as_stream(stream)>>>(work, cube_out, nx, ny, nv, t1, cube_in, t0);
     PNM_CUDA(cudaGetLastError());
     return PNM_OK;
 }

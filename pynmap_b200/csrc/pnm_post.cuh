@@ -333,9 +333,33 @@ struct Taps { double t[PNM_MAX_TAPS]; int n; };
 // one-output-per-thread loop would compute; zero fill = out-of-range loads return 0.
 constexpr int kSmoothOut = 4;
 
+// astropy's nan_treatment='interpolate' (the default of convolve, losvd.py:130-131) for ONE output voxel: NaN samples are
+// left out and the result is divided by the sum of the kernel values actually used (samples outside the array are the
+// fill value 0 and do count); an output whose every sample is NaN keeps the input value.  The 2-D kernel is the outer
+// product of the two normalised 1-D factors.  Only outputs that came out NaN from the separable passes get here.
+__device__ __noinline__ double smooth_nan2d(const double* __restrict__ orig, int nx, int ny, int nv, int ix, int iy, int iv,
+                                            const Taps& t0, const Taps& t1) {
+    const int r0 = t0.n / 2, r1 = t1.n / 2;
+    double top = 0.0, bot = 0.0;
+    for (int a = 0; a < t0.n; ++a) {
+        const int sx = ix + a - r0;
+        for (int b = 0; b < t1.n; ++b) {
+            const int sy = iy + b - r1;
+            const double ker = __dmul_rn(t0.t[a], t1.t[b]);
+            double val = 0.0;
+            if (sx >= 0 && sx < nx && sy >= 0 && sy < ny) val = orig[((int64_t)sx * ny + sy) * nv + iv];
+            if (val == val) { top = __fma_rn(val, ker, top); bot += ker; }
+        }
+    }
+    return bot == 0.0 ? orig[((int64_t)ix * ny + iy) * nv + iv] : __ddiv_rn(top, bot);
+}
+
+// AXIS 1 is the second pass: with ``orig`` (the cube the first pass read) it repairs the outputs that have a NaN in
+// their 2-D footprint (they come out NaN here) with smooth_nan2d.
 template <int AXIS>
 __global__ void __launch_bounds__(256) k_smooth_axis(const double* __restrict__ in, double* __restrict__ out,
-                                                     int nx, int ny, int nv, const __grid_constant__ Taps taps) {
+                                                     int nx, int ny, int nv, const __grid_constant__ Taps taps,
+                                                     const double* __restrict__ orig, const __grid_constant__ Taps taps_first) {
     // (the cube has < 2^31 voxels: checked at grid creation, so 32-bit indices are enough)
     const int len = AXIS == 0 ? nx : ny;
     const int nblk = (len + kSmoothOut - 1) / kSmoothOut;
@@ -345,9 +369,9 @@ __global__ void __launch_bounds__(256) k_smooth_axis(const double* __restrict__ 
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < items; i += stride) {
         const int iv = i % nv, rest = i / nv;
-        int pos0, base;                                 // first output position along AXIS, its flat index
+        int pos0, base, ixo = 0;                        // first output position along AXIS, its flat index
         if (AXIS == 0) { const int iy = rest % ny; pos0 = (rest / ny) * kSmoothOut; base = (pos0 * ny + iy) * nv + iv; }
-        else { const int b = rest % nblk; const int ix = rest / nblk; pos0 = b * kSmoothOut; base = (ix * ny + pos0) * nv + iv; }
+        else { const int b = rest % nblk; const int ix = rest / nblk; pos0 = b * kSmoothOut; base = (ix * ny + pos0) * nv + iv; ixo = ix; }
         auto at = [&](int p) -> double { return (p >= 0 && p < len) ? in[base + (p - pos0) * step] : 0.0; };
         double acc[kSmoothOut] = {0.0, 0.0, 0.0, 0.0};
         double w0 = at(pos0 - r), w1 = at(pos0 - r + 1), w2 = at(pos0 - r + 2), w3 = at(pos0 - r + 3);
@@ -362,7 +386,11 @@ __global__ void __launch_bounds__(256) k_smooth_axis(const double* __restrict__ 
         }
 #pragma unroll
         for (int j = 0; j < kSmoothOut; ++j)
-            if (pos0 + j < len) out[base + j * step] = acc[j];
+            if (pos0 + j < len) {
+                double v = acc[j];
+                if (AXIS == 1 && orig != nullptr && v != v) v = smooth_nan2d(orig, nx, ny, nv, ixo, pos0 + j, iv, taps_first, taps);
+                out[base + j * step] = v;
+            }
     }
 }
 

@@ -179,8 +179,9 @@ class PeerSlabReducer(SlabReducer):
                 t.zero_()
                 bufs.append(t)
             stage = [torch.empty(int(numel), dtype=dtype, device=device) for _ in range(2)]
+            ptrs = [(ctypes.c_void_p * self.world)(*[int(p) for p in h.buffer_ptrs]) for h in handles]
             ring = self._rings[key] = dict(bufs=bufs, handles=handles, stage=stage, next=0, step=0, pending=None, pulled=None,
-                                           cleared=[None] * self.nbuf)
+                                           ptrs=ptrs, index={b.data_ptr(): i for i, b in enumerate(bufs)})
         return ring
 
     def acquire(self, grid, acc):
@@ -195,8 +196,7 @@ class PeerSlabReducer(SlabReducer):
 
     def begin(self, acc_padded, grid, acc):
         ring = self._ring(acc_padded.numel(), acc_padded.dtype, acc_padded.device)
-        idx = [b.data_ptr() for b in ring["bufs"]].index(acc_padded.data_ptr())
-        handle = ring["handles"][idx]
+        idx = ring["index"][acc_padded.data_ptr()]
         per = self.chunk_slabs(grid) * grid.slab_elems
         cur = torch.cuda.current_stream()
         self._mark("begin", cur)
@@ -215,14 +215,10 @@ class PeerSlabReducer(SlabReducer):
         cs_ptr = ctypes.c_void_p(cs.cuda_stream)
         cs.wait_event(ready)
         ring["pending"] = acc_padded
-        # copy-engine pulls through the C ABI (cudaMemcpyAsync on the copy stream; a torch copy_ per chunk under a
-        # stream context costs ~20 us of host time each): own chunk first, then the peers in ring order
+        # copy-engine pulls through the C ABI: one call issues the cudaMemcpyAsync of every rank's chunk on the copy stream
         esz = acc_padded.element_size()
-        peers = handle.buffer_ptrs
-        for k in range(self.world):
-            p = (self.rank + k) % self.world
-            _lib.call("pnm_copy_async", ctypes.c_void_p(stage.data_ptr() + p * per * esz),
-                      ctypes.c_void_p(int(peers[p]) + self.rank * per * esz), per * esz, cs_ptr)
+        bases = ring["ptrs"][idx]
+        _lib.call("pnm_pull_chunks", ctypes.c_void_p(stage.data_ptr()), bases, self.world, self.rank, per * esz, cs_ptr)
         pulled = torch.cuda.Event()
         pulled.record(cs)
         self._mark("pulled", cs)

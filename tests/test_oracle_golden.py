@@ -182,3 +182,33 @@ def test_fixed_point_oracle():
     keep = (ix >= 0) & (iy >= 0)
     q = on.fixed_hist(iy.astype(np.int64) * 24 + ix, keep, w, scales[0], 24 * 24)
     assert np.array_equal(q.reshape(24, 24), a[0][0, :, :, 0])
+
+
+def test_convolve_nan_interpolate_known_answers():
+    """astropy.convolution.convolve defaults (boundary='fill', fill_value=0, nan_treatment='interpolate',
+    normalize_kernel=True), restated in oracle_np.convolve2d_fill0 and pnmo_smooth_cube.  astropy is absent, so these
+    known answers follow its documented algorithm (and its docstring example for the NaN-free case) -- the smoothing
+    row stays 'parity unpinned'."""
+    # NaN-free, zero fill (astropy docs: convolve([1, 4, 5, 6, 5, 7, 8], [0.2, 0.6, 0.2]) -> [1.4, 3.6, 5, 5.6, 5.6, 6.8, 6.2])
+    row = np.array([[1., 4., 5., 6., 5., 7., 8.]])
+    k = np.array([[0.2, 0.6, 0.2]])
+    want = np.array([[1.4, 3.6, 5.0, 5.6, 5.6, 6.8, 6.2]])
+    assert np.allclose(on.convolve2d_fill0(row, k), want, rtol=1e-14)
+    assert np.allclose(oc.smooth_cube(row[:, :, None], k)[:, :, 0], want, rtol=1e-14)
+    # a NaN sample is left out and the kernel renormalised over the samples used; the zero padding counts
+    row = np.array([[1., np.nan, 3.]])
+    k = np.array([[1., 1., 1.]]) / 3.0
+    want = np.array([[(0. + 1.) / 2., (1. + 3.) / 2., (3. + 0.) / 2.]])
+    assert np.allclose(on.convolve2d_fill0(row, k), want, rtol=1e-14)
+    assert np.allclose(oc.smooth_cube(row[:, :, None], k)[:, :, 0], want, rtol=1e-14)
+    # 2-D: centre NaN, 3 x 3 box -> mean of the 8 neighbours at the centre; corners use 3 real samples + 5 padded zeros
+    img = np.arange(1., 10.).reshape(3, 3)
+    img[1, 1] = np.nan
+    box = np.full((3, 3), 1. / 9.)
+    got = on.convolve2d_fill0(img, box)
+    assert np.isclose(got[1, 1], (1 + 2 + 3 + 4 + 6 + 7 + 8 + 9) / 8.)
+    assert np.isclose(got[0, 0], (1 + 2 + 4) / 8.)                # 3 samples + 5 zeros; the NaN is not counted
+    assert np.allclose(oc.smooth_cube(img[:, :, None], box)[:, :, 0], got, rtol=1e-14)
+    # every sample NaN -> the output keeps the input value (NaN): a 1 x 1 kernel on a NaN pixel
+    one = np.array([[np.nan, 2.]])
+    assert np.isnan(on.convolve2d_fill0(one, np.array([[1.]]))[0, 0]) and on.convolve2d_fill0(one, np.array([[1.]]))[0, 1] == 2.
