@@ -514,12 +514,10 @@ def test_tma_bulk_reduction_path_still_exact(pnm, monkeypatch):
     assert np.array_equal(ref[31][0], Mo) and np.array_equal(ref[31][1], Vo) and np.array_equal(ref[31][2], So, equal_nan=True)
 
 
-def test_smoothing_nan_interpolate_matches_oracle(env):
+def test_smoothing_nan_interpolate_matches_oracle(pnm):
     """convolve_spatial on a cube with NaN voxels (reachable: float64 accumulation propagates NaN weights into the cube):
     astropy's default nan_treatment='interpolate' -- NaN samples are skipped and the kernel renormalised per voxel; slices
     without NaNs are untouched by the repair path.  Against the C oracle (direct 2-D loop), 1e-10."""
-    pnm, wl = env
-    from pynmap_b200 import engine
     from pynmap_b200.losvd import LOSVD
     rng = np.random.default_rng(17)
     nx, ny, nv = 37, 29, 6
