@@ -64,15 +64,23 @@ def _convolve(array, kernel, boundary="fill", fill_value=0.0, **_):
 class _Table(dict):
     @classmethod
     def read(cls, filename, format=None, names=None, **_):
-        """Stand-in for astropy's Table.read(format='ascii').  Its basic reader takes the first line
-        as the header line even when ``names`` overrides the column names, so the first row of the
-        header-less SSP tables (misc_functions.py:223-226, :242-249) is consumed: 635 of 636 rows.
-        (astropy is absent here; this mirrors its documented behaviour and is an assumption.)"""
+        """Stand-in for astropy's Table.read(format='ascii', names=...).  Format guessing validates the first line as
+        a header BEFORE ``names`` is applied (astropy.io.ascii.core.BaseHeader.check_column_names with strict_names:
+        a token that looks like a number is not a column name), so a header-less numeric table such as the SSP files
+        (misc_functions.py:223-226, :242-249; first line 'Kb 1.30 -2.2653 ...') falls through to the no_header reader
+        and all 636 rows are data; a first line of words only is a header.  (astropy is absent here; this restates
+        its documented guessing rule.)"""
+        def is_number(tok):
+            try:
+                float(tok)
+                return True
+            except ValueError:
+                return False
         with open(filename) as fh:
-            header = fh.readline().lstrip("#").split()
-        if names is not None:
-            header = list(names)
-        data = np.loadtxt(filename, skiprows=1, dtype=str)
+            first = fh.readline().lstrip("#").split()
+        has_header = bool(first) and not any(is_number(t) for t in first)
+        header = list(names) if names is not None else (first if has_header else ["col%d" % (i + 1) for i in range(len(first))])
+        data = np.loadtxt(filename, skiprows=1 if has_header else 0, dtype=str)
         out = cls()
         for i, name in enumerate(header):
             col = data[:, i]

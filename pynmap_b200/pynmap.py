@@ -82,6 +82,61 @@ class SnapMap(object):
         return None
 
 
+class SnapMapList(list):
+    """A list of SnapMap with a free-text ``info`` (pynmap/pynmap.py:65-96): ``SnapMapList(maps, info=...)`` or
+    ``SnapMapList(map1, map2, ...)``; calling the list with keywords sets attributes."""
+
+    def __init__(self, *args, **kwargs):
+        items = args[0] if len(args) == 1 and hasattr(args[0], '__iter__') else args
+        super(SnapMapList, self).__init__(items)
+        self._info = ""
+        self(**kwargs)
+
+    def __call__(self, **kwargs):
+        if 'info' in kwargs:
+            self._info = kwargs.pop('info')
+        self.__dict__.update(kwargs)
+        return self
+
+    def update(self, **kwargs):
+        return self(**kwargs)
+
+    def info(self):
+        print(self._info)
+
+    def print(self):
+        for item in self:
+            print(item.name)
+
+
+class snapmap(object):
+    """A named 2-D array that can be written to / read from an ascii file (pynmap/pynmap.py:477-504)."""
+
+    def __init__(self, name="dummy", data=np.zeros((2, 2))):
+        self.name = name
+        self.data = data
+
+    def write_ascii(self, filename):
+        np.savetxt(filename, _to_numpy(self.data))
+
+    def read_ascii(self, filename):
+        self.data = np.loadtxt(filename)
+
+    def write_pickle(self, filename):
+        import pickle
+        with open(filename, 'wb') as f:
+            pickle.dump(_to_numpy(self.data), f)
+
+    def read_pickle(self, filename):
+        import pickle
+        with open(filename, 'rb') as f:
+            self.data = pickle.load(f)
+
+
+def _to_numpy(a):
+    return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+
+
 class PendingProjection(object):
     """What snapshot.project(deferred=True) returns: the scatter kernel has been launched; ``result()`` launches the
     reduction over ranks (if any) and the finalisation, once, and returns (SnapMap, LOSVD)."""

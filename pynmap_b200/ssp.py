@@ -179,9 +179,24 @@ MASS_COLS = ['IMF', 'slope', 'MH', 'age', 'mTot', 'mSRem', 'mS', 'mRem', 'mGas',
 PHOT_COLS = ['IMF', 'slope', 'MH', 'age', 'U', 'B', 'V', 'R', 'I', 'J', 'H', 'K']   # first 12 of 34 columns
 
 
+def _looks_like_number(tok):
+    try:
+        float(tok)
+        return True
+    except ValueError:
+        return False
+
+
 def _read_table(path, names):
-    """Whitespace ascii table with one header line (astropy Table.read(format='ascii') stand-in)."""
-    raw = np.loadtxt(path, dtype=str, comments=None, skiprows=1)
+    """Whitespace ascii table as astropy's Table.read(format='ascii', names=...) reads it (misc_functions.py:223-226,
+    :242-249).  Format guessing checks the FIRST line as a header before ``names`` is applied and rejects it when a
+    token looks like a number (astropy.io.ascii.core.BaseHeader.check_column_names with strict_names), falling
+    through to the no_header reader: the E-MILES tables have no header line ('Kb 1.30 -2.2653 ...'), so all 636 rows
+    are data.  A first line made of words only is taken as a header and skipped."""
+    with open(path) as fh:
+        first = fh.readline().split()
+    header = bool(first) and not any(_looks_like_number(t) for t in first)
+    raw = np.loadtxt(path, dtype=str, comments=None, skiprows=1 if header else 0)
     return {name: (raw[:, i].astype(np.float64) if i > 0 else raw[:, i]) for i, name in enumerate(names) if i < raw.shape[1]}
 
 

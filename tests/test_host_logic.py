@@ -110,3 +110,43 @@ def test_shard_bounds_and_span_helpers():
         assert cuts[0][0] == 0 and cuts[-1][1] == n
         assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:])) and all(lo <= hi for lo, hi in cuts)
         assert all(lo % sharded.ALIGN == 0 for lo, _ in cuts[1:] if lo < n)
+
+
+def test_dropin_pynmap_import_name():
+    """``dropin/`` on PYTHONPATH makes ``import pynmap`` (and its five submodules, pynmap/__init__.py:61) resolve to
+    pynmap_b200 -- checked in a child process so that this process can still import the real reference."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import pynmap, pynmap_b200\n"
+            "from pynmap.misc_functions import gausshermite, moment012, compute_ml, compute_ml_ssps\n"
+            "from pynmap.misc_io import convert_to_list, spread_amr, rebin_1darray, rebin_2darray, read_ascii_files\n"
+            "from pynmap import pynmap as p, grid, losvd, misc_io, misc_functions\n"
+            "assert p.snapshot is pynmap_b200.snapshot and losvd.LOSVD is pynmap_b200.LOSVD\n"
+            "assert grid.points_2vmaps is pynmap_b200.grid.points_2vmaps\n"
+            "print('ok')\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(root, "dropin"), root]))
+    out = subprocess.run([sys.executable, "-c", code], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout
+
+
+def test_misc_helpers_match_their_definitions():
+    """misc_io.rebin_1darray / rebin_2darray and misc_functions.moment012 (small host helpers of the drop-in surface)."""
+    import numpy as np
+    from pynmap_b200 import misc_functions, misc_io
+    a = np.arange(12.0)
+    assert np.array_equal(misc_io.rebin_1darray(a, 4), a.reshape(4, 3).sum(-1))
+    assert np.array_equal(misc_io.rebin_1darray(a, 3, 'mean'), a.reshape(3, 4).mean(-1))
+    b = np.arange(48.0).reshape(6, 8)
+    assert np.array_equal(misc_io.rebin_2darray(b, (3, 2)), b.reshape(3, 2, 2, 4).sum(-1).sum(1))
+    assert np.array_equal(misc_io.rebin_2darray(b, (2, 4), 'mean'), b.reshape(2, 3, 4, 2).mean(-1).mean(1))
+    x = np.linspace(-300., 300., 31)
+    d = np.exp(-0.5 * ((x - 40.) / 60.) ** 2)
+    m0, m1, m2 = misc_functions.moment012(x, d)
+    assert np.isclose(m0, d.sum()) and np.isclose(m1, (x * d).sum() / d.sum())
+    assert np.isclose(m2, np.sqrt((x * x * d).sum() / d.sum() - m1 ** 2))
+    assert misc_functions.moment012(x, np.zeros_like(x)) == (0., 0., 20. / 3.0)
+    assert misc_io.return_dummy(3, 1.5) == [1.5, 1.5, 1.5]
+    with __import__("pytest").raises(NotImplementedError):
+        misc_io.gas_to_cube(None, None, None, None, None)

@@ -164,7 +164,12 @@ def test_call_surface_matches_the_reference(ref):
         (ref.losvd.LOSVD.__init__, mine.LOSVD.__init__), (ref.losvd.LOSVD.convolve_spatial, mine.LOSVD.convolve_spatial),
         (ref.losvd.LOSVD.rebin_spatial, mine.LOSVD.rebin_spatial), (ref.losvd.LOSVD.vmoments, mine.LOSVD.vmoments),
         (ref.losvd.LOSVD.fitlosvd, mine.LOSVD.fitlosvd), (ref.fit_losvd.fitgh, mine.fit_losvd.fitgh),
-        (ref.misc_functions.gausshermite, mine.fit_losvd.gausshermite), (ref.misc_io.spread_amr, mine.amr.spread_amr),
+        (ref.misc_functions.gausshermite, mine.misc_functions.gausshermite), (ref.misc_io.spread_amr, mine.misc_io.spread_amr),
+        (ref.misc_functions.moment012, mine.misc_functions.moment012), (ref.misc_functions.compute_ml, mine.misc_functions.compute_ml),
+        (ref.misc_functions.compute_ml_ssps, mine.misc_functions.compute_ml_ssps),
+        (ref.misc_io.rebin_1darray, mine.misc_io.rebin_1darray), (ref.misc_io.rebin_2darray, mine.misc_io.rebin_2darray),
+        (ref.misc_io.read_ascii_files, mine.misc_io.read_ascii_files), (ref.misc_io.convert_to_list, mine.misc_io.convert_to_list),
+        (ref.misc_io.return_dummy, mine.misc_io.return_dummy),
         (ref.pynmap.snapshot.__init__, mine.snapshot.__init__), (ref.pynmap.snapshot.rotate, mine.snapshot.rotate),
         (ref.pynmap.snapshot.velocity_moments, mine.snapshot.velocity_moments),
         (ref.pynmap.snapshot.create_map, mine.snapshot.create_map),
@@ -182,3 +187,14 @@ def test_call_surface_matches_the_reference(ref):
             assert norm(got[k][1]) == norm(default), (ours.__qualname__, name, got[k][1], default)
         extra = [p for p in got[len(fixed):] if p[2] not in (inspect.Parameter.VAR_KEYWORD, inspect.Parameter.VAR_POSITIONAL)]
         assert all(p[1] != "<required>" for p in extra), (ours.__qualname__, extra)
+    # pynmap/__init__.py:61 -- `from . import pynmap, grid, misc_io, misc_functions, losvd`: the five submodules exist
+    # here under the same names, and every public function / class the reference defines in them has a namesake
+    # (implemented, or raising NotImplementedError for the parts SURVEY.md section 2 leaves out of scope)
+    import types
+    for sub in ("pynmap", "grid", "misc_io", "misc_functions", "losvd"):
+        theirs, ours = getattr(ref, sub), getattr(mine, sub)
+        for name, obj in vars(theirs).items():
+            if name.startswith("_") or getattr(obj, "__module__", None) != theirs.__name__:
+                continue
+            if isinstance(obj, (types.FunctionType, type)):
+                assert hasattr(ours, name), "%s.%s is missing" % (sub, name)

@@ -13,7 +13,7 @@ from oracle import oracle_np as on
 
 def test_oracle_reproduces_reference(golden):
     g = golden("ssp")
-    assert g["node_ML"].size == 635 and 0.06 < g["node_ML"].min() < g["node_ML"].max() < 8.7
+    assert g["node_ML"].size == 636 and 0.06 < g["node_ML"].min() < g["node_ML"].max() < 8.7
     ML = on.ml_from_nodes(g["node_age"], g["node_MH"], g["node_ML"], g["age"], g["MH"])
     assert np.array_equal(ML, g["ML"])                       # same scipy, same calls: bit-exact
     nofill = on.ml_from_nodes(g["node_age"], g["node_MH"], g["node_ML"], g["age"], g["MH"], fill_nan=False)
