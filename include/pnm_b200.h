@@ -294,6 +294,12 @@ int pnm_finalize_sums(const pnm_grid* g, const void* sums3, int acc_mode, const 
 int pnm_finalize_cube_slabs(const pnm_grid* g, const void* slabs, int32_t g0, int32_t g1, int acc_mode, double scale_w,
                             double* cube_out, void* stream);
 
+/* ---- is the snapshot stored in spatial order?  nsamples pairs of consecutive particles (i, i + 1), i = k * stride:
+ * out2_dev[0] = pairs closer than `limit`, out2_dev[1] = pairs examined (device, uint64).  The host layer picks the
+ * accumulator layout from it (ordered snapshots merge consecutive particles in registers: pnm_project_bin). ------- */
+int pnm_order_probe(const void* x, const void* y, const void* z, int64_t n, int dtype, int64_t stride, int64_t nsamples,
+                    double limit, uint64_t* out2_dev, void* stream);
+
 /* ---- max |a[i]| over n elements -> out_dev[0] (float64, device); used to pick FIXED scales -- */
 int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream);
 

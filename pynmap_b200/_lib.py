@@ -71,6 +71,7 @@ _SIGNATURES = {
     "pnm_slab_sums": (c_int, [_P, _P, c_int32, c_int32, c_int, _P, _P]),
     "pnm_finalize_sums": (c_int, [_P, _P, c_int, POINTER(c_double), _P, _P, _P, _P]),
     "pnm_finalize_cube_slabs": (c_int, [_P, _P, c_int32, c_int32, c_int, c_double, _P, _P]),
+    "pnm_order_probe": (c_int, [_P, _P, _P, c_int64, c_int, c_int64, c_int64, c_double, _P, _P]),
     "pnm_cube_slots_max": (c_int32, []),
     "pnm_cube_plan_create": (c_int, [_P, POINTER(_P)]),
     "pnm_cube_plan_destroy": (c_int, [_P]),

@@ -723,6 +723,22 @@ int pnm_ct_interp(const void* qx, const void* qy, int64_t n, int dtype, const do
     return PNM_OK;
 }
 
+int pnm_order_probe(const void* x, const void* y, const void* z, int64_t n, int dtype, int64_t stride, int64_t nsamples,
+                    double limit, uint64_t* out2_dev, void* stream) {
+    if (!out2_dev || n < 0 || stride < 1 || nsamples < 0 || (n > 0 && (!x || !y || !z))) return fail(PNM_EINVAL, "pnm_order_probe: bad argument");
+    PNM_CUDA(cudaMemsetAsync(out2_dev, 0, 2 * sizeof(uint64_t), as_stream(stream)));
+    if (n < 2 || nsamples == 0) return PNM_OK;
+    const int grid = (int)((nsamples + 255) / 256);
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(out2_dev);
+    if (dtype == PNM_F32)
+        pnm::k_order_probe<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, (const float*)y, (const float*)z, n, stride, nsamples, limit * limit, out);
+    else if (dtype == PNM_F64)
+        pnm::k_order_probe<double><<<grid, 256, 0, as_stream(stream)>>>((const double*)x, (const double*)y, (const double*)z, n, stride, nsamples, limit * limit, out);
+    else return fail(PNM_EDTYPE, "pnm_order_probe: dtype %d", dtype);
+    PNM_CUDA(cudaGetLastError());
+    return PNM_OK;
+}
+
 int pnm_absmax(const void* a, int64_t n, int dtype, double* out_dev, void* stream) {
     if (!out_dev || n < 0 || (n > 0 && !a)) return fail(PNM_EINVAL, "pnm_absmax: bad argument");
     PNM_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double), as_stream(stream)));

@@ -505,6 +505,29 @@ __global__ void __launch_bounds__(256) k_ct_interp(const T* __restrict__ qx, con
     }
 }
 
+// ---------------------------------------------------------------- memory-order probe
+// Is the snapshot stored in a spatial order (tree / space-filling curve)?  Sample pairs of CONSECUTIVE particles
+// (i, i + 1), i = k * stride: out[0] counts the pairs closer than `limit`, out[1] the pairs looked at.  "The median
+// distance is below one pixel" <=> more than half of the pairs are closer than a pixel -- a count, no sort.
+template <typename T>
+__global__ void __launch_bounds__(256) k_order_probe(const T* __restrict__ x, const T* __restrict__ y, const T* __restrict__ z,
+                                                     int64_t n, int64_t stride, int64_t nsamples, double limit2,
+                                                     unsigned long long* out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool close = false, looked = false;
+    if (k < nsamples) {
+        const int64_t i = k * stride;
+        if (i + 1 < n) {
+            const double dx = (double)x[i + 1] - (double)x[i], dy = (double)y[i + 1] - (double)y[i], dz = (double)z[i + 1] - (double)z[i];
+            const double d2 = dx * dx + dy * dy + dz * dz;
+            looked = true;
+            close = d2 < limit2;                      // NaN distances are not close
+        }
+    }
+    const unsigned c = __popc(__ballot_sync(0xffffffffu, close)), l = __popc(__ballot_sync(0xffffffffu, looked));
+    if ((threadIdx.x & 31) == 0 && l) { atomicAdd(out, (unsigned long long)c); atomicAdd(out + 1, (unsigned long long)l); }
+}
+
 // ---------------------------------------------------------------- abs-max (fixed-point scale)
 // Non-negative doubles order like their bit patterns, so one integer atomicMax per block suffices.
 template <typename T>

@@ -1,6 +1,8 @@
 """Device engine behind the pynmap call surface: grids, accumulators and the calls into
 libpnm_b200.so.  torch is used for device memory, streams and (in sharded.py) the
-process group only -- every arithmetic step of the path is a kernel of the library.
+process group and symmetric memory -- every arithmetic step of the projection path (rotate, bin, reduce over ranks,
+finalise, smooth, and the probes that pick scales / layouts) is a kernel of the library.  What is left to torch: dtype
+conversions and copies at ingestion, clearing accumulators, and the one-off per-snapshot flux = mass / ML division.
 
 Layout in HBM
   particles     SoA, one contiguous array per coordinate (x, y, z, vx, vy, vz, w)
@@ -248,6 +250,19 @@ def absmax(t):
     out = torch.empty(1, dtype=torch.float64, device=t.device)
     _lib.call("pnm_absmax", ptr(t), t.numel(), _TORCH_TO_PNM[t.dtype], ptr(out), stream_ptr())
     return float(out.item())
+
+
+def order_probe(x, y, z, limit, nsamples=65536):
+    """pnm_order_probe: (pairs of consecutive particles closer than ``limit``, pairs examined) on a strided sample --
+    one small kernel and one 16-byte read."""
+    n = x.numel()
+    out = torch.empty(2, dtype=torch.int64, device=x.device)
+    stride = max(1, (n - 1) // max(1, nsamples))
+    nsamp = min(nsamples, max(0, (n - 1 + stride - 1) // stride))
+    _lib.call("pnm_order_probe", ptr(x), ptr(y), ptr(z), n, _TORCH_TO_PNM[x.dtype], stride, nsamp, float(limit), ptr(out),
+              stream_ptr())
+    close, looked = (int(v) for v in out.tolist())
+    return close, looked
 
 
 # ----------------------------------------------------------------------------- the scatter

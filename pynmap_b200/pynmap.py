@@ -716,18 +716,17 @@ class snapshot(object):
 
     def _memory_ordered(self, grid, reducer=None):
         """True when neighbours in memory are neighbours in space (median distance between consecutive particles
-        below one pixel), estimated once per snapshot and pixel size on a strided sample of 65536 pairs.  Sharded
+        below one pixel), estimated once per snapshot and pixel size on a strided sample of 65536 pairs by one small
+        kernel of the library (pnm_order_probe: a count of close pairs, no sort).  Sharded
         runs agree on one answer (any rank ordered -> all use the plain layout): the partial grids are summed."""
         pos = self._base[0]
         pix = min((grid.limXY[1] - grid.limXY[0]) / max(grid.nx - 1, 1), (grid.limXY[3] - grid.limXY[2]) / max(grid.ny - 1, 1))
         key = ("ordered", float(pix), id(reducer))
         if key not in self._absmax:
-            n = self.npart
             ordered = False
-            if n >= 8192:
-                idx = torch.arange(0, n - 1, max(1, (n - 1) // 65536), device=pos[0].device)
-                d2 = sum((pos[k][idx + 1] - pos[k][idx]).double() ** 2 for k in range(3))
-                ordered = bool(torch.sqrt(d2).median().item() < pix)
+            if self.npart >= 8192:
+                close, looked = engine.order_probe(pos[0], pos[1], pos[2], pix)
+                ordered = looked > 0 and 2 * close > looked      # median distance below one pixel, without a sort
             if reducer is not None:
                 ordered = bool(reducer.reduce_max(float(ordered))[0] > 0.5)
             self._absmax[key] = ordered
