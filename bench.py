@@ -276,6 +276,43 @@ def parity_check(pnm, engine, workloads, snap, soa, reducer, rank, world, n_loca
                    else "the snapshot in one launch vs two ragged half shards (%d + %d particles) into one accumulator" % tuple(pieces)}
 
 
+def c3_point(pnm, workloads, reducer, rank, world, sink, n_total=1_000_000_000, nxy=512):
+    """BASELINE.json configs[2]: n_total particles sharded over the ranks, nxy x nxy M / V / sigma maps, partial grids
+    combined by an NCCL all-reduce.  Single passes (no pipelining), timed with CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    n_local = n_total // world
+    soa = workloads.make_snapshot(n_local, bulge_fraction=0.2, seed=SEED + 2 + 1000 * rank, device="cuda")
+    snap = pnm.snapshot.from_arrays(soa[:3], soa[3:6], mass=soa[6], output="torch")
+    del soa
+    snap.rotate(PA=PA, inclination=INCL)
+
+    def one():
+        with contextlib.redirect_stdout(sink):
+            vm = snap.velocity_moments(weight_name="mass", limXY=workloads.LIM_XY, nXY=nxy, reducer=reducer)
+        sink.seek(0); sink.truncate()
+        return vm
+
+    for _ in range(3):
+        one()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    reps = 10
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        vm = one()
+    b.record(); torch.cuda.synchronize()
+    ms = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    binned = float(vm.M.sum().item())
+    del snap
+    torch.cuda.empty_cache()
+    return {"workload": "%.3g particles over %d GPUs (%.3g per GPU), %dx%d M/V/sigma maps, all-reduce of the partial grids; "
+                        "one non-pipelined pass" % (n_total, world, n_local, nxy, nxy),
+            "ms_per_pass": ms, "value": n_local * world / (ms * 1e-3), "unit": "particles/s", "particles_binned": binned}
+
+
 def big_point(pnm, engine, workloads, n, peak, sink, accumulate):
     """10^9 particles resident on ONE GPU: the same pipelined step, 5 timed steps after 3 warm-up steps."""
     import torch
@@ -535,6 +572,12 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
 
+    # ---- BASELINE.json config 3 at N > 1: 10^9 particles over 8 GPUs (1.25e8 per GPU), 512 x 512 moment maps, NCCL
+    # all-reduce of the partial grids; ONE pass, nothing pipelined: the latency a user of velocity_moments() sees
+    c3 = None
+    if world > 1 and not args.no_extras:
+        c3 = c3_point(pnm, workloads, GridReducer(all_ranks=True), rank, world, sink)
+
     # ---- the north star's single-GPU size: 10^9 particles resident on one B200 (28 GB), same grid, same step
     if extras is not None and not args.no_1e9 and n_local < BIG_N:
         del snap, soa
@@ -595,7 +638,7 @@ def run_b200(args):
             "clocks": clocks,
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "parity": parity,
-            "extras": extras,
+            "extras": extras if c3 is None else dict(extras or {}, c3=c3),
         }
         print(json.dumps(line))
     if world > 1:

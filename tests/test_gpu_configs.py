@@ -382,3 +382,43 @@ def test_pipelined_project_recycles_accumulators_correctly(env):
             for a, b in ((vm0.M, vm.M), (vm0.V, vm.V), (vm0.S, vm.S), (lv0.losvd, lv.losvd)):
                 assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
         assert len(next(iter(snap._acc_pool.values()))) == 2          # two sets in rotation
+
+
+def test_velocity_moments_with_reducer_hook(env):
+    """velocity_moments(reducer=...) (BASELINE config 3: maps only, partial grids summed over ranks): the reducer sees
+    ONE folded map replica; two particle shards whose partial grids are added give the bits of the whole snapshot with
+    int64 accumulators; a rank that does not hold the total gets None."""
+    pnm, wl = env
+    n = 300_000
+    soa = wl.make_snapshot(n, seed=91, device="cuda", unit_mass=False)
+    bounds = (float(soa[6].abs().max()), 2.0 * max(float(soa[k].abs().max()) for k in (3, 4, 5)))
+    kw = dict(weight_name="mass", limXY=wl.LIM_XY, nXY=[72, 56], accumulate="fixed")
+
+    def snap_of(lo, hi):
+        s = pnm.snapshot.from_arrays(soa[:3, lo:hi], soa[3:6, lo:hi], mass=soa[6, lo:hi], output="torch")
+        s.rotate(PA=30., inclination=60.)
+        return s
+
+    class Hook(object):
+        def __init__(self, keep=None, add=None):
+            self.keep, self.add, self.seen = keep, add, []
+        def n_total(self, n_local): return n
+        def reduce_max(self, *v): return bounds
+        def __call__(self, *tensors):
+            self.seen.append([t.numel() for t in tensors])
+            if self.keep is not None:
+                self.keep.extend(t.clone() for t in tensors)
+                return False
+            for t, o in zip(tensors, self.add or []):
+                t += o
+            return True
+
+    whole_hook = Hook()
+    whole = snap_of(0, n).velocity_moments(reducer=whole_hook, **kw)
+    assert whole_hook.seen == [[72 * 56 * 4]]                 # one folded replica of 4 slots per pixel
+    kept = []
+    assert snap_of(0, 120_008).velocity_moments(reducer=Hook(keep=kept), **kw) is None
+    both = snap_of(120_008, n).velocity_moments(reducer=Hook(add=kept), **kw)
+    for a, b in ((both.M, whole.M), (both.V, whole.V), (both.S, whole.S)):
+        assert torch.equal(torch.nan_to_num(a, nan=-1.0), torch.nan_to_num(b, nan=-1.0))
+    assert float(whole.M.sum()) > 0
