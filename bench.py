@@ -170,7 +170,13 @@ class ClockSampler(object):
     def __init__(self, index, period_ms=20):
         import shutil
         import subprocess
-        self.proc, self.ok = None, False
+        self.proc, self.ok, self.first, self.extra, self.nvml = None, False, "", [], None
+        try:                                                 # NVML handle for sample_now() (no polling thread)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
+        except Exception:
+            self.nvml = None
         exe = shutil.which("nvidia-smi")
         if exe is None:
             return
@@ -181,21 +187,13 @@ class ClockSampler(object):
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.first = self.proc.stdout.readline()         # blocks until the child is polling (driver start-up)
             self.ok = bool(self.first.strip())
-            self.nvml = None
-            try:                                             # one more sample from this process, see sample_now()
-                import pynvml
-                pynvml.nvmlInit()
-                self.nvml = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(index))
-            except Exception:
-                pass
-            self.extra = []
         except Exception:
             self.proc = None
 
     def sample_now(self):
         """One NVML sample taken by the launching thread itself (called right after the last launch of the timed
         region, while the GPU is still working through the queue)."""
-        if self.ok and self.nvml is not None:
+        if self.nvml is not None:
             try:
                 nv, h = self.nvml
                 get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
@@ -204,19 +202,18 @@ class ClockSampler(object):
                 pass
 
     def stop(self):
-        if not self.ok:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        self.proc.terminate()
-        try:
-            out, _ = self.proc.communicate(timeout=5)
-        except Exception:
-            self.proc.kill()
-            out = ""
+        out = ""
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
         samples, mask, max_mhz = [c for c, _ in self.extra], 0, None
         for _, m in self.extra:
             mask |= m
-        lines = out.splitlines()
-        for line in (lines if lines else [self.first]):      # (the first sample was taken before the timed region)
+        lines = out.splitlines() if self.ok else []
+        for line in (lines if lines else ([self.first] if self.ok else [])):      # (the first sample was taken before the timed region)
             parts = [p.strip() for p in line.split(",")]
             try:
                 samples.append(float(parts[0]))
@@ -224,6 +221,11 @@ class ClockSampler(object):
                 mask |= int(parts[2], 16)
             except Exception:
                 continue
+        if max_mhz is None and self.nvml is not None:
+            try:
+                max_mhz = float(self.nvml[0].nvmlDeviceGetMaxClockInfo(self.nvml[1], self.nvml[0].NVML_CLOCK_SM))
+            except Exception:
+                pass
         reasons = [name for bit, name in self.REASONS.items() if mask & bit]
         return {"sm_mhz": float(np.median(samples)) if samples else None, "sm_max_mhz": max_mhz,
                 "reasons": reasons, "samples": len(samples), "sampler": "nvidia-smi -lms 20 (child process) + one NVML read after the last launch"}

@@ -84,7 +84,7 @@ constexpr int kCubeSmemBytes = 227 * 1024;
 // Every array ends with 32 dummy entries, one per lane, for the lanes that have nothing to add.
 constexpr int kPmStride = (kBoxPix + 32) * 4;     // bytes from the sum w*d array to the sum w*d*d array
 constexpr int kCubeSmemFixed = kBoxPix * 4 + 2 * kPmStride + kCubeWarps * kQueueCap * 16;
-constexpr int kCubeSlotsMax = (kCubeSmemBytes - kCubeSmemFixed) / 4 - 32;
+constexpr int kCubeSlotsMax = (kCubeSmemBytes - kCubeSmemFixed) / 4 - 32 - 4;   // 32 dummy entries + 4 words of carry constants behind the slots
 #ifndef PNM_CUBE_TYP_BITS
 #define PNM_CUBE_TYP_BITS 24
 #endif
@@ -226,10 +226,12 @@ __device__ __forceinline__ typename AccT<ACC>::type to_acc_f(float v, float scal
     return (typename AccT<ACC>::type)(is_finite(s) ? __float2ll_rn(s) : 0ll);
 }
 
-// h carries out of a low limb, as a value of the global accumulator: h * 2^32 (int64) or h * 2^32 * 2^-k (float64, exact)
+// h = +-1 carried out of a low limb, as a value of the global accumulator: h * 2^32 (int64) or h * 2^32 * 2^-k (float64).
+// 2^32 * 2^-k is a power of two: `hi` is the high word of that double (low word 0, staged in shared memory by the
+// prologue), the sign of h goes into its sign bit -- no conversion, no multiplication, no load from the plan.
 template <int ACC>
-__device__ __forceinline__ typename AccT<ACC>::type carry_value(int h, double inv_scale) {
-    if (ACC == PNM_ACC_F64) return (typename AccT<ACC>::type)((double)h * 4294967296.0 * inv_scale);
+__device__ __forceinline__ typename AccT<ACC>::type carry_value(int h, uint32_t hi) {
+    if (ACC == PNM_ACC_F64) return (typename AccT<ACC>::type)__hiloint2double((int)(hi ^ ((uint32_t)h & 0x80000000u)), 0);
     return (typename AccT<ACC>::type)((long long)h << 32);
 }
 
@@ -257,6 +259,8 @@ __global__ void __launch_bounds__(kCubeThreads, 1) k_project_cube(const __grid_c
     for (int i = threadIdx.x; i < 2 * (kBoxPix + 32); i += kCubeThreads) s_pm[i] = 0u;
     for (int i = threadIdx.x; i < nslots; i += kCubeThreads) s_ws[i] = 0u;
     if (threadIdx.x < 32) s_ws[kCubeSlotsMax + threadIdx.x] = 0u;
+    if (threadIdx.x < 3)                                         // carry constants: high word of the double 2^32 * 2^-k
+        s_ws[kCubeSlotsMax + 32 + threadIdx.x] = (uint32_t)__double2hiint(4294967296.0 * (ACC == PNM_ACC_F64 ? plan->inv_smem[threadIdx.x] : 1.0));
     if (nbox == 0 && threadIdx.x == 0) s_tab[0] = 0u;           // entry 0 is read by lanes outside the box
     __syncthreads();
 
@@ -293,6 +297,7 @@ __global__ void __launch_bounds__(kCubeThreads, 1) k_project_cube(const __grid_c
     const uint32_t a_tab = a_smem, a_pm = a_smem + kBoxPix * 4, a_ws = a_smem + kCubeSmemFixed;
     const uint32_t a_queue = a_smem + kBoxPix * 4 + 2 * kPmStride + (unsigned)warp * (kQueueCap * 16);
     const unsigned pm_dummy = (unsigned)(kBoxPix + lane), ws_dummy = (unsigned)(kCubeSlotsMax + lane);   // this lane's dummy entries
+    const uint32_t a_carry = a_ws + 4u * (unsigned)(kCubeSlotsMax + 32);
     unsigned lt_mask;
     asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lt_mask));
 #if PNM_CUBE_PIN
@@ -406,9 +411,9 @@ __global__ void __launch_bounds__(kCubeThreads, 1) k_project_cube(const __grid_c
 #pragma unroll
             for (int k = 0; k < kG; ++k) {
                 A* const rest = cube + ((int64_t)(G2 >> 1) * npix + pix[k]) * 4;
-                if (h1[k]) red_add(rest + 2, carry_value<ACC>(h1[k], plan->inv_smem[1]));
-                if (h2[k]) red_add(rest + 3, carry_value<ACC>(h2[k], plan->inv_smem[2]));
-                if (h0[k]) red_add(cube + rec[k], carry_value<ACC>(h0[k], plan->inv_smem[0]));
+                if (h1[k]) red_add(rest + 2, carry_value<ACC>(h1[k], lds_u32(a_carry + 4u)));
+                if (h2[k]) red_add(rest + 3, carry_value<ACC>(h2[k], lds_u32(a_carry + 8u)));
+                if (h0[k]) red_add(cube + rec[k], carry_value<ACC>(h0[k], lds_u32(a_carry)));
             }
         }
         if (q_tail - q_head >= 128u) {
