@@ -789,10 +789,10 @@ class snapshot(object):
         like rotate(reset=True).  Returns a list of SnapMap.
 
         ``views_per_launch`` > 1 bins several views per read of the particles (pnm_project_bin with
-        nviews > 1).  The default is one launch per view: the scatter is bound by reduction issue,
-        not by HBM, so re-reading the particles is free, while 64 views' accumulators (134 MB at
-        256x256) no longer fit in L2 -- measured 24.8 ms (64 launches) vs 43.4 ms (one launch) for
-        2e7 particles."""
+        nviews > 1).  The default is one launch per view: re-reading the particles costs far less than
+        the scatter itself, and the multi-view kernel gives up the one-request-per-particle packing of
+        the single-view maps path -- measured 14.9 ms (64 launches) vs 24.5 / 25.2 / 43.2 ms (2 / 8 / 64
+        views per launch) for 2e7 particles x 64 views (profiles/r02_micro_views_bench.log)."""
         if weight_name is not None:
             weights = self._select_weight(weight_name)
         n2 = engine.expand_nxy(nXY)

@@ -1,10 +1,17 @@
 """Particle-sharded multi-GPU execution (new: the reference is single process).
 
-One process per GPU.  The path shards naturally: every rank bins a contiguous slice of the
-particles into its own full-size accumulators (no halo, no sorting) and the only exchange is a
-SUM of those partial grids -- `torch.distributed.reduce` (NCCL over NVLink on the GPU box, gloo
-in the CPU tests).  With int64 fixed-point accumulators the reduced grids are bit-identical for
-any number of ranks, because integer addition is associative.
+One process per GPU.  The path shards naturally: every rank bins a contiguous slice of the particles into its own
+full-size accumulators (no halo, no sorting) and the only exchange is a SUM of those partial grids.  Three flavours:
+
+  GridReducer       reduce / all-reduce of the whole partial grids (NCCL on the GPU box, gloo in the CPU tests): one rank
+                    (or every rank) finalises everything.  velocity_moments(reducer=) and the host path use it.
+  SlabReducer       reduce-scatter along the record slabs (pairs of velocity bins) of the interleaved cube: every rank
+                    finalises and smooths its own velocity bins, the maps come from an all-reduce of per-rank shares.
+  PeerSlabReducer   the same exchange without NCCL kernels or SMs: accumulators in symmetric memory, copy-engine pulls over
+                    NVLink that run under the next scatter kernel (snapshot.project(deferred=True)), local sum in rank order.
+
+With int64 fixed-point accumulators the reduced grids are bit-identical for any number of ranks and any flavour, because
+integer addition is associative (bench.py checks it on hardware every run).
 """
 import ctypes
 import os
