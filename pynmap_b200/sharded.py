@@ -216,7 +216,12 @@ class PeerSlabReducer(SlabReducer):
         self._mark("zeroed", cur)
         ready = torch.cuda.Event()
         ready.record(cur)
-        stage = ring["stage"][ring["step"] % 2]
+        si = ring["step"] % 2
+        if ring.setdefault("busy", [False, False])[si]:
+            raise RuntimeError("PeerSlabReducer: more than two projections in flight -- call result() of the older "
+                               "pending projections first (their staged chunks would be overwritten)")
+        ring["busy"][si] = True
+        stage = ring["stage"][si]
         ring["step"] += 1
         cs = self._copy_stream
         cs_ptr = ctypes.c_void_p(cs.cuda_stream)
@@ -230,7 +235,7 @@ class PeerSlabReducer(SlabReducer):
         pulled.record(cs)
         self._mark("pulled", cs)
         ring["pulled"] = pulled
-        return (stage, pulled, per, acc)
+        return (stage, pulled, per, acc, ring, si)
 
     def finish(self, token):
         from . import engine
@@ -239,6 +244,7 @@ class PeerSlabReducer(SlabReducer):
         cur.wait_event(pulled)
         self._mark("finish", cur)
         out = engine.sum_chunks(stage, self.world, per, acc)
+        token[4]["busy"][token[5]] = False               # (stream order protects the staged chunks from here on)
         self._mark("summed", cur)
         return out
 
