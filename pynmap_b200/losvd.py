@@ -158,7 +158,8 @@ class LOSVD(object):
         # the reference deep-copies (losvd.py:118): the new object shares nothing with this one -- the coordinate arrays
         # are copied here, the cube and its uncertainties are replaced below
         closvd = copy.copy(self)
-        closvd.binx, closvd.biny, closvd.binv = (copy.deepcopy(a) for a in (self.binx, self.biny, self.binv))
+        closvd.binx, closvd.biny, closvd.binv = (a.copy() if isinstance(a, np.ndarray) else copy.deepcopy(a)
+                                                 for a in (self.binx, self.biny, self.binv))
         print("LOSVD FWHM: XLOS[{0}] YLOS[{1}]".format(self.fwhmx, self.fwhmy))
         print("Starting the Convolution to reach FWHM: XCLOS[{0}] YCLOS[{1}]".format(
               reached_fwhmx, reached_fwhmy))
