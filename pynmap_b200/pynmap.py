@@ -741,8 +741,8 @@ class snapshot(object):
                 ordered = looked > 0 and 2 * close > looked      # median distance below one pixel, without a sort
             if reducer is not None:
                 ordered = bool(reducer.reduce_max(float(ordered))[0] > 0.5)
-            self._absmax[key] = ordered
-        return self._absmax[key]
+            self._absmax[key] = (ordered, reducer)       # (the reducer is held so that its id stays unique)
+        return self._absmax[key][0]
 
     def _project_post(self, grid, maps, cube, sums, acc, scales, reducer):
         """Everything after the scatter of project(): fold + reduce over ranks, finalisation."""
