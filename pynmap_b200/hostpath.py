@@ -47,22 +47,24 @@ def project_host(arrays, PA, inclination, limXY, nXY, limV=None, nV=0, accumulat
     """arrays = (x, y, z, vx, vy, vz, w-or-None) on the host, one dtype.  Returns a dict with
     float64 host arrays M, V, S (nY, nX) and, when nV > 0, cube (nX, nY, nV) -- or None on ranks
     that do not hold the reduced result.  ``out`` may provide preallocated (pinned) outputs."""
-    _lib.require_device()
-    device = torch.cuda.current_device() if device is None else int(device)
-    n2 = engine.expand_nxy(nXY)
-    nx, ny, nv = n2[0], n2[1], int(nV or 0)
+    # argument checks first (they need no device): the C ABI only sees pointers, so a shorter or differently typed
+    # array would be read out of bounds
+    if len(arrays) != 7 or any(a is None for a in arrays[:6]):
+        raise ValueError("host path wants (x, y, z, vx, vy, vz, w-or-None)")
     x = arrays[0]
     n = int(x.shape[0])
     code = _dtype_code(x)
-    if len(arrays) != 7 or any(a is None for a in arrays[:6]):
-        raise ValueError("host path wants (x, y, z, vx, vy, vz, w-or-None)")
-    for a in arrays:        # the C ABI only sees pointers: a shorter or differently typed array would be read out of bounds
+    for a in arrays:
         if a is not None and (a.dtype != x.dtype or tuple(a.shape) != (n,)):
             raise ValueError("host path: every array must be 1-D with %d entries of dtype %s, got shape %s dtype %s"
                              % (n, x.dtype, tuple(a.shape), a.dtype))
     acc = engine.AccMode(accumulate)
     if acc.code == _lib.ACC_FIXED and scales is None:
         raise ValueError("fixed-point host path needs explicit scales (engine.fixed_scales)")
+    n2 = engine.expand_nxy(nXY)
+    nx, ny, nv = n2[0], n2[1], int(nV or 0)
+    _lib.require_device()
+    device = torch.cuda.current_device() if device is None else int(device)
     mat = np.ascontiguousarray(rotation_matrix(np.float32(PA), np.float32(inclination)).reshape(9))
     matp = mat.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
     ex = engine.bin_edges(limXY[0], limXY[1], nx)
