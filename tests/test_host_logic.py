@@ -150,3 +150,32 @@ def test_misc_helpers_match_their_definitions():
     assert misc_io.return_dummy(3, 1.5) == [1.5, 1.5, 1.5]
     with __import__("pytest").raises(NotImplementedError):
         misc_io.gas_to_cube(None, None, None, None, None)
+
+
+def test_low_limb_carry_scheme_of_the_privatised_kernel():
+    """The arithmetic k_project_cube (csrc/pnm_cube.cuh) uses for its shared-memory sums, restated with numpy: a signed
+    32-bit term a is added to an unsigned 32-bit low limb (ATOMS.ADD returns the old value); the adding thread owes the
+    high part h = (a >> 31) + carry_out(old + a), which is -1, 0 or +1 and is sent to the global accumulator as
+    h * 2^32.  Low limb + 2^32 * sum(h) must equal the exact 64-bit sum for any order of the terms."""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    for scale in (2 ** 24, 2 ** 30, 2 ** 31 - 1):
+        a = rng.integers(-scale, scale, 20000, dtype=np.int64)
+        a[:10] = [scale - 1, -(scale - 1), 0, 1, -1, scale - 1, scale - 1, -(scale - 1), -(scale - 1), 5]
+        for order in (np.arange(a.size), rng.permutation(a.size)):
+            low, high = 0, 0
+            for t in a[order].tolist():
+                old = low
+                low = (old + t) & 0xFFFFFFFF                           # ATOMS.ADD on the low limb (two's complement)
+                carry = 1 if old + (t & 0xFFFFFFFF) > 0xFFFFFFFF else 0   # add.cc.u32 of old and the term's low word
+                h = (-1 if t < 0 else 0) + carry                       # addc.s32 with the sign extension of the term
+                assert h in (-1, 0, 1)
+                high += h
+            assert low + (high << 32) == int(a.sum())
+    # float64 accumulators: h * 2^32 * 2^-k is built from the high word of the double 2^(32-k) and the sign of h
+    import struct
+    for k in (-20, 0, 11, 24, 40):
+        hi = struct.unpack("<q", struct.pack("<d", 4294967296.0 * 2.0 ** -k))[0] >> 32
+        for h in (1, -1):
+            word = (hi ^ ((h & 0xFFFFFFFF) & 0x80000000)) << 32
+            assert struct.unpack("<d", struct.pack("<q", word if word < 2 ** 63 else word - 2 ** 64))[0] == h * 2.0 ** (32 - k)
