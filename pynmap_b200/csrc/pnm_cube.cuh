@@ -41,7 +41,9 @@
 //   over the records of a pixel; pnm_finalize_vmaps sums them over g), record (G, pixel) = the same for particles
 //   outside the V range (slot 0) and the flushed shared-memory moments (slots 2, 3).
 //
-// What bounds it (ncu, round 2, profiles/r02_ncu_cube_*.txt).  The first version executed 180 warp instructions per
+// What bounds it (ncu, round 2; the final kernel is summarised in profiles/r02_ncu_full_summary.txt: 162 warp
+// instructions per 32 particles, 67 % issue utilisation, 0.45 L2 reduction requests per particle, DRAM traffic 1.008 x
+// the algorithmic bytes).  The first version executed 180 warp instructions per
 // particle at 72 % issue utilisation and kept the LSU data pipe 84 % busy (l1tex__data_pipe_lsu_wavefronts): per warp
 // and particle 20 wavefronts of shared atomics (the { low, high } pairs put every low limb into 8 or 16 of the 32
 // banks), 14 of particle loads (a no-allocate LDG.128 delivers 64 bytes per wavefront), 7 of REDs, 5 of table
